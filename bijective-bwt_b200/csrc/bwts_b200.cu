@@ -1,0 +1,696 @@
+// bwts_b200.cu -- C ABI of libbwts_b200.so and the host-side drivers of the two hot paths.
+//
+// forward  (replaces /root/reference/mk_bwts_sa.c:47-52):  Lyndon boundaries -> packed
+//          initial keys -> onesweep sort -> prefix-doubling rounds -> emit
+// inverse  (replaces /root/reference/unbwts.c:31-86):      tile counts -> LF map -> splitter
+//          walks -> reduced-list ranking -> offsets scan -> placement
+// There is no CPU fallback anywhere in this file: without a device every call fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/bwts_b200.h"
+#include "common.cuh"
+#include "forward.cuh"
+#include "inverse.cuh"
+#include "lyndon.cuh"
+#include "radix.cuh"
+#include "scan.cuh"
+
+#define BWTS_VERSION "bwts-b200 0.1 (sm_100a)"
+
+enum KClass {
+    KC_LYNDON = 0, KC_FACTORS, KC_INIT_KEYS, KC_RADIX_HIST, KC_ONESWEEP, KC_BUILD_KEYS, KC_RERANK, KC_EMIT,
+    KC_INV_HIST, KC_INV_LF, KC_INV_WALK, KC_INV_JUMP, KC_INV_SCAN, KC_INV_PLACE, KC_MISC, KC_COPY
+};
+static const char *kclass_names[BWTS_B200_NCLASS] = {
+    "lyndon", "factor_table", "init_keys", "radix_hist", "onesweep_pass", "build_keys", "rerank", "emit",
+    "inv_tile_hist", "inv_lf_rank", "inv_walk", "inv_jump", "inv_scan", "inv_place", "misc", "copy"};
+
+static long g_tune_chunk = 0;      // Lyndon chunk bytes (0 = auto)
+static long g_tune_spl_shift = 0;  // splitter shift   (0 = 26)
+
+struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; };
+
+struct bwts_b200_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    u8 *arena = nullptr;
+    size_t arena_bytes = 0, arena_used = 0;
+    u8 *io_in = nullptr, *io_out = nullptr;  // device staging of the host-buffer API
+    size_t io_bytes = 0;
+    u32 *h_small = nullptr;  // pinned, 4 KiB, for counter read-backs
+    int last_cuda = 0;
+    bool profile = true;
+    std::vector<LaunchRec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_used = 0;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bwts_b200_stats stats;
+    u32 epoch = 0;
+};
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) {                                                 \
+            ctx->last_cuda = (int)e__;                                            \
+            return (e__ == cudaErrorMemoryAllocation) ? BWTS_B200_ENOMEM : BWTS_B200_ECUDA; \
+        }                                                                         \
+    } while (0)
+
+static cudaEvent_t ctx_event(bwts_b200_ctx *ctx)
+{
+    if (ctx->pool_used == ctx->pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->pool.push_back(e);
+    }
+    return ctx->pool[ctx->pool_used++];
+}
+
+// LAUNCH(class, algorithmic bytes, kernel, grid, block, args...)
+#define LAUNCH(KCLS_, NBYTES_, kern, grid, block, ...)                               \
+    do {                                                                             \
+        LaunchRec r__;                                                               \
+        r__.cls = (KCLS_); r__.bytes = (double)(NBYTES_); r__.e0 = r__.e1 = nullptr; \
+        if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); } \
+        kern<<<(grid), (block), 0, st>>>(__VA_ARGS__);                               \
+        if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
+        ctx->recs.push_back(r__);                                                    \
+        CK(cudaGetLastError());                                                      \
+    } while (0)
+
+static void stats_begin(bwts_b200_ctx *ctx, long len, int direction, cudaStream_t st)
+{
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.len = len;
+    ctx->stats.direction = direction;
+    ctx->recs.clear();
+    ctx->pool_used = 0;
+    cudaEventRecord(ctx->ev_begin, st);
+}
+static void stats_end(bwts_b200_ctx *ctx, cudaStream_t st)
+{
+    cudaEventRecord(ctx->ev_end, st);
+    cudaEventSynchronize(ctx->ev_end);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
+    ctx->stats.total_ms = ms;
+    ctx->stats.launches = (long)ctx->recs.size();
+    for (const LaunchRec &r : ctx->recs) {
+        ctx->stats.class_launches[r.cls]++;
+        ctx->stats.class_bytes[r.cls] += r.bytes;
+        if (r.e0 && r.e1) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) ctx->stats.class_ms[r.cls] += t;
+        }
+    }
+}
+
+// ---- arena ---------------------------------------------------------------------------------
+static int arena_reserve(bwts_b200_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->arena_bytes) return 0;
+    if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+    CK(cudaMalloc((void **)&ctx->arena, bytes));
+    ctx->arena_bytes = bytes;
+    return 0;
+}
+template <typename T>
+static T *arena_take(bwts_b200_ctx *ctx, size_t count)
+{
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (ctx->arena_used + bytes > ctx->arena_bytes) return nullptr;
+    T *p = (T *)(ctx->arena + ctx->arena_used);
+    ctx->arena_used += bytes;
+    return p;
+}
+static size_t workspace_bytes(size_t n)
+{
+    // forward is the larger of the two: keys 2x8, idx/grp/gst 2x4 each, rank 4, FS 4,
+    // flags 1, onesweep status n/2, misc
+    return n * 72 + (64u << 20);
+}
+
+static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+static inline int bit_length(u64 v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
+
+static int readback(bwts_b200_ctx *ctx, cudaStream_t st, const void *dptr, size_t bytes)
+{
+    CK(cudaMemcpyAsync(ctx->h_small, dptr, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- radix sort driver ------------------------------------------------------------------------
+struct SortBufs {
+    u64 *k[2];
+    u32 *v[2];
+    int cur;        // index of the buffers holding the data
+    u32 *hist;      // [8][256] + 8 tickets
+    u64 *status;    // tiles * 256
+};
+
+static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, int passes, bool identity_vals)
+{
+    if (passes < 1) passes = 1;
+    if (passes > RADIX_MAX_PASSES) return BWTS_B200_EINTERNAL;
+    CK(cudaMemsetAsync(sb.hist, 0, (RADIX_MAX_PASSES * RADIX_BINS + RADIX_MAX_PASSES) * sizeof(u32), st));
+    u32 *tickets = sb.hist + RADIX_MAX_PASSES * RADIX_BINS;
+    const u32 hgrid = min(cdiv(m, 256), 148u * 8u);
+    LAUNCH(KC_RADIX_HIST, 8.0 * m, k_radix_hist, hgrid, 256, sb.k[sb.cur], m, passes, sb.hist);
+    LAUNCH(KC_RADIX_HIST, 0, k_radix_hist_scan, passes, 256, sb.hist);
+    const u32 tiles = cdiv(m, OS_TILE);
+    for (int p = 0; p < passes; p++) {
+        const int a = sb.cur, b = sb.cur ^ 1;
+        const bool ident = identity_vals && p == 0;
+        ctx->epoch = (ctx->epoch + 1) & 0x3fffffffu;
+        if (ctx->epoch == 0) ctx->epoch = 1;
+        LAUNCH(KC_ONESWEEP, (ident ? 20.0 : 24.0) * m, k_onesweep_pass, tiles, OS_NT, sb.k[a],
+               ident ? (const u32 *)nullptr : sb.v[a], sb.k[b], sb.v[b], m, (u32)(p * RADIX_BITS),
+               sb.hist + p * RADIX_BINS, sb.status, tickets + p, ctx->epoch);
+        sb.cur = b;
+        ctx->stats.radix_passes++;
+    }
+    return 0;
+}
+
+// ---- forward ---------------------------------------------------------------------------------
+// linear != 0: suffix-array mode (successor i+1, end of text smallest) -- fills d_sa instead of d_out.
+static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 *d_sa, int linear, cudaStream_t st)
+{
+    int rc = arena_reserve(ctx, workspace_bytes(n));
+    if (rc) return rc;
+    ctx->arena_used = 0;
+    if (ctx->io_in && ctx->io_in == dT) ctx->arena_used = ((size_t)2 * ctx->io_bytes + 511) & ~(size_t)255;
+
+    const u32 ntl = cdiv(n, FL_TILE);
+    const u32 nblk = cdiv(n, 1u << COARSE_BITS);
+    const u32 os_tiles = cdiv(n, OS_TILE), rr_tiles = cdiv(n, RR_TILE);
+
+    SortBufs sb;
+    sb.k[0] = arena_take<u64>(ctx, n);
+    sb.k[1] = arena_take<u64>(ctx, n);
+    sb.v[0] = arena_take<u32>(ctx, n);
+    sb.v[1] = arena_take<u32>(ctx, n);
+    sb.cur = 0;
+    sb.hist = arena_take<u32>(ctx, RADIX_MAX_PASSES * RADIX_BINS + RADIX_MAX_PASSES);
+    sb.status = arena_take<u64>(ctx, (size_t)os_tiles * RADIX_BINS);
+    u32 *grp[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
+    u32 *gst[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
+    u32 *rank = arena_take<u32>(ctx, n);
+    u32 *FS = arena_take<u32>(ctx, (size_t)n + 1);
+    u32 *cidx = arena_take<u32>(ctx, (size_t)nblk + 2);
+    u8 *flags = arena_take<u8>(ctx, n);
+    u32 *tilecnt = arena_take<u32>(ctx, ntl + 1);
+    u64 *rr_status = arena_take<u64>(ctx, rr_tiles + 1);
+    u32 *small = arena_take<u32>(ctx, 1024);  // [0] F, [1] lmax, [2] sigma, [8..15] presence, [16..] rerank counters
+    u8 *code = (u8 *)arena_take<u32>(ctx, 64);
+    if (!sb.k[0] || !sb.k[1] || !sb.v[0] || !sb.v[1] || !sb.hist || !sb.status || !grp[0] || !grp[1] || !gst[0] ||
+        !gst[1] || !rank || !FS || !cidx || !flags || !tilecnt || !rr_status || !small || !code)
+        return BWTS_B200_EINTERNAL;
+    RerankCounters *rrc = (RerankCounters *)(small + 16);
+
+    CK(cudaMemsetAsync(small, 0, 1024 * sizeof(u32), st));
+    u32 F = 1, lmax = n;
+
+    if (!linear) {
+        // -- Lyndon boundaries
+        u32 chunk = g_tune_chunk > 0 ? (u32)g_tune_chunk : max(2048u, cdiv(n, 65536));
+        const u32 nch = cdiv(n, chunk), ngroups = cdiv(nch, LY_GROUP);
+        u32 *chunk_last = arena_take<u32>(ctx, nch);
+        u32 *group_min = arena_take<u32>(ctx, ngroups);
+        u32 *group_excl = arena_take<u32>(ctx, ngroups);
+        if (!chunk_last || !group_min || !group_excl) return BWTS_B200_EINTERNAL;
+        CK(cudaMemsetAsync(flags, 0, n, st));
+        LAUNCH(KC_LYNDON, 2.0 * n, k_duval_chunks, cdiv(nch, 128), 128, dT, n, chunk, nch, flags, chunk_last);
+        if (nch > 1) {
+            LAUNCH(KC_LYNDON, 0, k_chunkmin_reduce, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk_last, nch,
+                   group_min, ngroups);
+            LAUNCH(KC_LYNDON, 0, k_chunkmin_scan, 1, 1024, dT, n, group_min, ngroups, group_excl);
+            LAUNCH(KC_LYNDON, 0, k_chunk_threshold, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk, nch, flags,
+                   chunk_last, group_excl, ngroups);
+        }
+        // -- factor table
+        LAUNCH(KC_FACTORS, 1.0 * n, k_flag_count, ntl, 256, flags, n, tilecnt);
+        LAUNCH(KC_FACTORS, 8.0 * ntl, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, ntl, small + 0);
+        LAUNCH(KC_FACTORS, 1.0 * n, k_flag_write, ntl, 256, flags, n, tilecnt, FS);
+        LAUNCH(KC_FACTORS, 0, k_set_u32, 1, 1, FS, small + 0, n);
+    }
+    // -- alphabet
+    LAUNCH(KC_INIT_KEYS, 1.0 * n, k_byte_presence, min(cdiv(n, 16 * 256) + 1, 148u * 8u), 256, dT, n, small + 8);
+    LAUNCH(KC_INIT_KEYS, 0, k_code_table, 1, 256, small + 8, code, small + 2);
+    rc = readback(ctx, st, small, 16);
+    if (rc) return rc;
+    const u32 sigma = ctx->h_small[2];
+    if (!linear) {
+        F = ctx->h_small[0];
+        if (F < 1 || F > n) return BWTS_B200_EINTERNAL;
+        LAUNCH(KC_FACTORS, 4.0 * F, k_factor_lmax, min(cdiv(F, 256), 148u * 4u), 256, FS, F, small + 1);
+        LAUNCH(KC_FACTORS, 4.0 * nblk, k_coarse_index, cdiv(nblk + 1, 256), 256, FS, F, cidx, nblk);
+    }
+    const u32 syms = linear ? sigma + 1 : sigma;  // linear mode reserves code 0 for "past the end"
+    const u32 bits = max(1, bit_length(syms - 1));
+    const u32 k0 = 64 / bits;
+    const int P0 = (int)cdiv((u64)k0 * bits, 8);
+    ctx->stats.alphabet_bits = (int)bits;
+    ctx->stats.initial_depth = (int)k0;
+
+    if (!linear) {
+        LAUNCH(KC_INIT_KEYS, 9.0 * n, k_init_keys, cdiv(cdiv(n, 8), 256), 256, dT, n, FS, cidx, code, bits, k0,
+               sb.k[0]);
+    } else {
+        LAUNCH(KC_INIT_KEYS, 9.0 * n, k_init_keys_linear, cdiv(cdiv(n, 8), 256), 256, dT, n, code, bits, k0, sb.k[0]);
+    }
+    rc = radix_sort(ctx, st, sb, n, P0, true);
+    if (rc) return rc;
+
+    CK(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
+    CK(cudaMemsetAsync(grp[0], 0, (size_t)n * 4, st));
+    CK(cudaMemsetAsync(gst[0], 0, (size_t)n * 4, st));
+
+    int g = 0;  // current grp/gst buffers
+    u32 m = n, groups_before = 1;
+    u64 k = k0;
+    const u32 kb = linear ? bit_length(n) : max(1, bit_length((u64)n - 1));
+    bool first = true;
+    for (;;) {
+        // re-rank the freshly sorted live array, compact
+        CK(cudaMemsetAsync(rr_status, 0, (size_t)cdiv(m, RR_TILE) * 8, st));
+        CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
+        LAUNCH(KC_RERANK, 24.0 * m, k_rerank, cdiv(m, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur], grp[g], gst[g], m,
+               0, rank, sb.v[sb.cur ^ 1], grp[g ^ 1], gst[g ^ 1], rr_status, rrc);
+        rc = readback(ctx, st, rrc, sizeof(RerankCounters));
+        if (rc) return rc;
+        const RerankCounters c = *(const RerankCounters *)ctx->h_small;
+        ctx->stats.class_bytes[KC_RERANK] += 12.0 * c.kept;
+        if (first && !linear) {
+            rc = readback(ctx, st, small + 1, 4);
+            if (rc) return rc;
+            lmax = ctx->h_small[0];
+            first = false;
+        }
+        const bool split = c.heads != groups_before;
+        // adopt the compacted arrays
+        sb.cur ^= 1;  // idx now lives in v[cur]; k[cur] is scratch for the next key build
+        g ^= 1;
+        m = c.kept;
+        groups_before = c.kheads;
+        if (m == 0) break;
+        const bool deep_enough = !linear && k >= 2ull * lmax;  // Fine-Wilf: remaining ties are equal rotations
+        if (!split || deep_enough) {
+            if (linear) return BWTS_B200_EINTERNAL;  // suffixes are pairwise distinct
+            // ties are final: give every member of a tie its own slot
+            CK(cudaMemsetAsync(rr_status, 0, (size_t)cdiv(m, RR_TILE) * 8, st));
+            CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
+            LAUNCH(KC_RERANK, 16.0 * m, k_rerank, cdiv(m, RR_TILE), RR_NT, (const u64 *)nullptr, sb.v[sb.cur], grp[g],
+                   gst[g], m, 1, rank, (u32 *)nullptr, (u32 *)nullptr, (u32 *)nullptr, rr_status, rrc);
+            break;
+        }
+        // one doubling round on the live set
+        ctx->stats.rounds++;
+        ctx->stats.live_sum += m;
+        if (!linear) {
+            LAUNCH(KC_BUILD_KEYS, 20.0 * m, k_build_keys, cdiv(m, 256), 256, sb.v[sb.cur], gst[g], m, rank, FS, cidx,
+                   (u32)k, kb, sb.k[sb.cur]);
+        } else {
+            LAUNCH(KC_BUILD_KEYS, 20.0 * m, k_build_keys_linear, cdiv(m, 256), 256, sb.v[sb.cur], gst[g], m, rank, n,
+                   (u32)k, kb, sb.k[sb.cur]);
+        }
+        const int passes = (int)cdiv((u64)kb + max(1, bit_length((u64)m - 1)), 8);
+        rc = radix_sort(ctx, st, sb, m, passes, false);
+        if (rc) return rc;
+        k *= 2;
+    }
+
+    // -- emit
+    if (!linear) {
+        LAUNCH(KC_EMIT, 7.0 * n, k_emit, cdiv(n, 256), 256, dT, n, rank, flags, d_out);
+        LAUNCH(KC_EMIT, 10.0 * F, k_emit_heads, cdiv(F, 256), 256, dT, FS, F, rank, d_out);
+    } else {
+        LAUNCH(KC_EMIT, 8.0 * n, k_emit_sa, cdiv(n, 256), 256, rank, n, d_sa);
+    }
+    ctx->stats.factors = F;
+    ctx->stats.longest_factor = lmax;
+    return 0;
+}
+
+// ---- inverse -----------------------------------------------------------------------------------
+static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cudaStream_t st)
+{
+    int rc = arena_reserve(ctx, workspace_bytes(n));
+    if (rc) return rc;
+    ctx->arena_used = 0;
+    if (ctx->io_in && ctx->io_in == dB) ctx->arena_used = ((size_t)2 * ctx->io_bytes + 511) & ~(size_t)255;
+
+    const u32 shift = g_tune_spl_shift ? (u32)g_tune_spl_shift : 26u;
+    const u32 ntiles = cdiv(n, INV_TILE), nchunks = cdiv(ntiles, INV_CHUNK);
+    const u32 nst = cdiv(n, SP_TILE), nsc = cdiv(n, SC_TILE);
+
+    u32 *tilehist = arena_take<u32>(ctx, (size_t)ntiles * 256);
+    u32 *chunksum = arena_take<u32>(ctx, (size_t)nchunks * 256);
+    u32 *prev = arena_take<u32>(ctx, n);
+    uint2 *rec = arena_take<uint2>(ctx, n);
+    u32 *len_at_min = arena_take<u32>(ctx, n);
+    u32 *off = arena_take<u32>(ctx, n);
+    uint2 *cyc = arena_take<uint2>(ctx, n);
+    u32 *tilecnt = arena_take<u32>(ctx, max(nst, nsc) + 1);
+    u32 *small = arena_take<u32>(ctx, 64);
+    if (!tilehist || !chunksum || !prev || !rec || !len_at_min || !off || !cyc || !tilecnt || !small)
+        return BWTS_B200_EINTERNAL;
+    CK(cudaMemsetAsync(small, 0, 64 * sizeof(u32), st));
+
+    // -- LF map
+    LAUNCH(KC_INV_HIST, 1.0 * n, k_inv_tile_hist, ntiles, INV_NT, dB, n, tilehist);
+    LAUNCH(KC_INV_SCAN, 1024.0 * ntiles, k_inv_colsum, nchunks, 256, tilehist, ntiles, chunksum);
+    LAUNCH(KC_INV_SCAN, 0, k_inv_chunk_scan, 1, 256, chunksum, nchunks);
+    LAUNCH(KC_INV_SCAN, 2048.0 * ntiles, k_inv_tile_base, nchunks, 256, tilehist, ntiles, chunksum);
+    LAUNCH(KC_INV_LF, 5.0 * n, k_inv_lf_rank, ntiles, INV_NT, dB, n, tilehist, prev);
+
+    // -- splitters
+    CK(cudaMemsetAsync(rec, 0xff, (size_t)n * sizeof(uint2), st));
+    CK(cudaMemsetAsync(len_at_min, 0, (size_t)n * 4, st));
+    LAUNCH(KC_INV_WALK, 0, k_inv_spl_count, nst, 256, n, shift, tilecnt);
+    LAUNCH(KC_INV_SCAN, 8.0 * nst, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, nst, small + 0);
+    rc = readback(ctx, st, small, 4);
+    if (rc) return rc;
+    const u32 ns = ctx->h_small[0];
+    if (ns < 1 || ns > n) return BWTS_B200_EINTERNAL;
+    u32 *spl = arena_take<u32>(ctx, ns);
+    u64 *jm[3] = {arena_take<u64>(ctx, ns), arena_take<u64>(ctx, ns), arena_take<u64>(ctx, ns)};
+    u64 *pv[2] = {arena_take<u64>(ctx, ns), arena_take<u64>(ctx, ns)};
+    u32 *wlen = arena_take<u32>(ctx, ns);
+    uint2 *minfo = arena_take<uint2>(ctx, ns);
+    uint4 *srec = arena_take<uint4>(ctx, ns);
+    if (!spl || !jm[0] || !jm[1] || !jm[2] || !pv[0] || !pv[1] || !wlen || !minfo || !srec) return BWTS_B200_EINTERNAL;
+    LAUNCH(KC_INV_WALK, 12.0 * ns, k_inv_spl_write, nst, 256, n, shift, tilecnt, spl, rec);
+    LAUNCH(KC_INV_WALK, 12.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, rec, jm[0], wlen, minfo);
+
+    // -- reduced list: cycle minimum, then distance to the sublist holding it
+    const int R = bit_length((u64)ns - 1) + 1;
+    const u32 gs = cdiv(ns, 256);
+    int cur = 0;
+    for (int r = 0; r < R; r++) {
+        const int dst = (cur == 1) ? 2 : 1;
+        LAUNCH(KC_INV_JUMP, 24.0 * ns, k_inv_min_jump, gs, 256, jm[cur], jm[dst], ns);
+        cur = dst;
+    }
+    u64 *jmR = jm[cur];
+    LAUNCH(KC_INV_JUMP, 32.0 * ns, k_inv_sum_init, gs, 256, jm[0], jmR, wlen, minfo, ns, pv[0]);
+    int pc = 0;
+    for (int r = 0; r < R; r++) {
+        LAUNCH(KC_INV_JUMP, 24.0 * ns, k_inv_sum_jump, gs, 256, pv[pc], pv[pc ^ 1], ns);
+        pc ^= 1;
+    }
+    LAUNCH(KC_INV_JUMP, 24.0 * ns, k_inv_origin_publish, gs, 256, jmR, pv[pc], minfo, ns, len_at_min, cyc);
+    LAUNCH(KC_INV_WALK, 8.0 * n, k_inv_self_walk, cdiv(n, 256), 256, prev, n, rec, len_at_min, small + 4);
+
+    // -- offsets of the cycles, in order of ascending smallest index
+    LAUNCH(KC_INV_SCAN, 4.0 * n, k_tile_sum_u32, nsc, 256, len_at_min, n, tilecnt);
+    LAUNCH(KC_INV_SCAN, 8.0 * nsc, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, nsc, small + 8);
+    LAUNCH(KC_INV_SCAN, 8.0 * n, k_tile_scan_apply_u32, nsc, 256, len_at_min, off, n, tilecnt);
+    LAUNCH(KC_INV_SCAN, 4.0 * n, k_inv_count_cycles, min(cdiv(n, 256), 148u * 8u), 256, len_at_min, n, small + 6);
+
+    // -- placement
+    LAUNCH(KC_INV_PLACE, 44.0 * ns, k_inv_spl_record, gs, 256, jmR, pv[pc], cyc, off, ns, srec);
+    LAUNCH(KC_INV_PLACE, 14.0 * n, k_inv_place, cdiv(n, 256), 256, dB, n, rec, srec, off, d_out);
+
+    rc = readback(ctx, st, small, 40);
+    if (rc) return rc;
+    if (ctx->h_small[8] != n) return BWTS_B200_EINTERNAL;  // cycle lengths must add up to n
+    ctx->stats.splitters = ns;
+    ctx->stats.unreached = ctx->h_small[4];
+    ctx->stats.factors = ctx->h_small[6];
+    return 0;
+}
+
+// ---- contexts -------------------------------------------------------------------------------------
+extern "C" int bwts_b200_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+extern "C" bwts_b200_ctx *bwts_b200_create(int device)
+{
+    if (device < 0 || device >= bwts_b200_device_count()) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    bwts_b200_ctx *ctx = new bwts_b200_ctx();
+    ctx->device = device;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->h_small, 4096, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_begin) != cudaSuccess || cudaEventCreate(&ctx->ev_end) != cudaSuccess) {
+        bwts_b200_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+extern "C" void bwts_b200_destroy(bwts_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
+    for (cudaEvent_t e : ctx->pool) cudaEventDestroy(e);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->io_in) cudaFree(ctx->io_in);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    delete ctx;
+}
+
+extern "C" int bwts_b200_reserve(bwts_b200_ctx *ctx, long max_len)
+{
+    if (!ctx || max_len <= 0) return BWTS_B200_EINVAL;
+    if (max_len > BWTS_B200_MAX_LEN) return BWTS_B200_ETOOBIG;
+    CK(cudaSetDevice(ctx->device));
+    return arena_reserve(ctx, workspace_bytes((size_t)max_len));
+}
+
+static int check_len(const void *in, long len, void *out)
+{
+    if (!in || !out || len <= 0) return BWTS_B200_EINVAL;
+    if (len > BWTS_B200_MAX_LEN) return BWTS_B200_ETOOBIG;
+    return 0;
+}
+
+static int run_device(bwts_b200_ctx *ctx, int direction, const void *d_in, long len, void *d_out, void *stream)
+{
+    if (!ctx) return BWTS_B200_EINVAL;
+    int rc = check_len(d_in, len, d_out);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->own_stream;
+    stats_begin(ctx, len, direction, st);
+    rc = direction == 0 ? forward_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, nullptr, 0, st)
+                        : inverse_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, st);
+    if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
+    stats_end(ctx, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; return BWTS_B200_ECUDA; }
+    return 0;
+}
+
+extern "C" int bwts_b200_forward_device(bwts_b200_ctx *ctx, const void *d_in, long len, void *d_out, void *stream)
+{
+    return run_device(ctx, 0, d_in, len, d_out, stream);
+}
+extern "C" int bwts_b200_inverse_device(bwts_b200_ctx *ctx, const void *d_in, long len, void *d_out, void *stream)
+{
+    return run_device(ctx, 1, d_in, len, d_out, stream);
+}
+
+static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, long len, unsigned char *out)
+{
+    if (!ctx) return BWTS_B200_EINVAL;
+    int rc = check_len(in, len, out);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    // workspace first (it may have to be re-allocated), then the two I/O buffers in its first bytes
+    rc = arena_reserve(ctx, workspace_bytes((size_t)len) + 2 * (size_t)len + 1024);
+    if (rc) return rc;
+    ctx->io_bytes = ((size_t)len + 255) & ~(size_t)255;
+    ctx->io_in = nullptr;
+    u8 *d_in = ctx->arena, *d_out = ctx->arena + ctx->io_bytes;
+    cudaStream_t st = ctx->own_stream;
+    CK(cudaMemcpyAsync(d_in, in, (size_t)len, cudaMemcpyHostToDevice, st));
+    ctx->io_in = d_in;  // tells the cores to skip the I/O region of the arena
+    stats_begin(ctx, len, direction, st);
+    rc = direction == 0 ? forward_core(ctx, d_in, (u32)len, d_out, nullptr, 0, st)
+                        : inverse_core(ctx, d_in, (u32)len, d_out, st);
+    ctx->io_in = nullptr;
+    if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
+    stats_end(ctx, st);
+    CK(cudaMemcpyAsync(out, d_out, (size_t)len, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int bwts_b200_forward_host(bwts_b200_ctx *ctx, const unsigned char *in, long len, unsigned char *out)
+{
+    return run_host(ctx, 0, in, len, out);
+}
+extern "C" int bwts_b200_inverse_host(bwts_b200_ctx *ctx, const unsigned char *in, long len, unsigned char *out)
+{
+    return run_host(ctx, 1, in, len, out);
+}
+
+// ---- one-call entry points ---------------------------------------------------------------------------
+#define MAX_DEV 64
+static std::mutex g_dev_mutex[MAX_DEV];
+static bwts_b200_ctx *g_dev_ctx[MAX_DEV];
+
+static int with_default_ctx(int device, int direction, const unsigned char *in, long len, unsigned char *out)
+{
+    int rc = check_len(in, len, out);
+    if (rc) return rc;
+    const int ndev = bwts_b200_device_count();
+    if (ndev == 0) return BWTS_B200_ENODEV;
+    if (device < 0 || device >= ndev || device >= MAX_DEV) return BWTS_B200_EINVAL;
+    std::lock_guard<std::mutex> lock(g_dev_mutex[device]);
+    if (!g_dev_ctx[device]) g_dev_ctx[device] = bwts_b200_create(device);
+    if (!g_dev_ctx[device]) return BWTS_B200_ENODEV;
+    return run_host(g_dev_ctx[device], direction, in, len, out);
+}
+
+extern "C" int bwts_b200_forward(const unsigned char *in, long len, unsigned char *out, int device)
+{
+    return with_default_ctx(device, 0, in, len, out);
+}
+extern "C" int bwts_b200_inverse(const unsigned char *in, long len, unsigned char *out, int device)
+{
+    return with_default_ctx(device, 1, in, len, out);
+}
+
+static int run_blocks(int direction, const unsigned char *in, long len, long block_len, unsigned char *out,
+                      const int *devices, int ndev)
+{
+    if (!in || !out || len <= 0 || ndev < 1) return BWTS_B200_EINVAL;
+    if (block_len <= 0 || block_len > len) block_len = len;
+    if (block_len > BWTS_B200_MAX_LEN) return BWTS_B200_ETOOBIG;
+    const int have = bwts_b200_device_count();
+    if (have == 0) return BWTS_B200_ENODEV;
+    std::vector<int> dev(ndev);
+    for (int i = 0; i < ndev; i++) {
+        dev[i] = devices ? devices[i] : i;
+        if (dev[i] < 0 || dev[i] >= have) return BWTS_B200_EINVAL;
+    }
+    const long nblocks = (len + block_len - 1) / block_len;
+    std::vector<int> status(ndev, 0);
+    std::vector<std::thread> workers;
+    for (int w = 0; w < ndev; w++) {
+        workers.emplace_back([&, w]() {
+            bool any = false;
+            for (long b = w; b < nblocks; b += ndev) { any = true; break; }
+            if (!any) return;
+            bwts_b200_ctx *ctx = bwts_b200_create(dev[w]);
+            if (!ctx) { status[w] = BWTS_B200_ENODEV; return; }
+            for (long b = w; b < nblocks && status[w] == 0; b += ndev) {
+                const long o = b * block_len;
+                const long l = (o + block_len <= len) ? block_len : len - o;
+                status[w] = run_host(ctx, direction, in + o, l, out + o);
+            }
+            bwts_b200_destroy(ctx);
+        });
+    }
+    for (std::thread &t : workers) t.join();
+    for (int w = 0; w < ndev; w++)
+        if (status[w]) return status[w];
+    return 0;
+}
+
+extern "C" int bwts_b200_forward_blocks(const unsigned char *in, long len, long block_len, unsigned char *out,
+                                        const int *devices, int ndev)
+{
+    return run_blocks(0, in, len, block_len, out, devices, ndev);
+}
+extern "C" int bwts_b200_inverse_blocks(const unsigned char *in, long len, long block_len, unsigned char *out,
+                                        const int *devices, int ndev)
+{
+    return run_blocks(1, in, len, block_len, out, devices, ndev);
+}
+
+// ---- suffix array behind libdivsufsort's seam ------------------------------------------------------
+extern "C" int bwts_b200_divsufsort(const unsigned char *T, int *SA, int n, int device)
+{
+    if (!T || !SA || n < 0) return BWTS_B200_EINVAL;
+    if (n == 0) return 0;
+    if ((long)n > BWTS_B200_MAX_LEN) return BWTS_B200_ETOOBIG;
+    const int ndev = bwts_b200_device_count();
+    if (ndev == 0) return BWTS_B200_ENODEV;
+    if (device < 0 || device >= ndev || device >= MAX_DEV) return BWTS_B200_EINVAL;
+    std::lock_guard<std::mutex> lock(g_dev_mutex[device]);
+    if (!g_dev_ctx[device]) g_dev_ctx[device] = bwts_b200_create(device);
+    bwts_b200_ctx *ctx = g_dev_ctx[device];
+    if (!ctx) return BWTS_B200_ENODEV;
+    CK(cudaSetDevice(device));
+    const size_t io = ((size_t)n + 255) & ~(size_t)255;
+    const size_t sa_bytes = ((size_t)n * 4 + 255) & ~(size_t)255;
+    int rc = arena_reserve(ctx, workspace_bytes((size_t)n) + io + sa_bytes + 1024);
+    if (rc) return rc;
+    // I/O region: text, then the suffix array
+    ctx->io_bytes = (io + sa_bytes + 1) / 2;
+    ctx->io_bytes = (ctx->io_bytes + 255) & ~(size_t)255;
+    u8 *d_in = ctx->arena;
+    i32 *d_sa = (i32 *)(ctx->arena + io);
+    cudaStream_t st = ctx->own_stream;
+    CK(cudaMemcpyAsync(d_in, T, (size_t)n, cudaMemcpyHostToDevice, st));
+    ctx->io_in = d_in;
+    stats_begin(ctx, n, 0, st);
+    rc = forward_core(ctx, d_in, (u32)n, nullptr, d_sa, 1, st);
+    ctx->io_in = nullptr;
+    if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
+    stats_end(ctx, st);
+    CK(cudaMemcpyAsync(SA, d_sa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- introspection --------------------------------------------------------------------------------------
+extern "C" int bwts_b200_get_stats(const bwts_b200_ctx *ctx, bwts_b200_stats *out)
+{
+    if (!ctx || !out) return BWTS_B200_EINVAL;
+    *out = ctx->stats;
+    return 0;
+}
+extern "C" const char *bwts_b200_class_name(int cls)
+{
+    return (cls >= 0 && cls < BWTS_B200_NCLASS) ? kclass_names[cls] : nullptr;
+}
+extern "C" int bwts_b200_set_profile(bwts_b200_ctx *ctx, int on)
+{
+    if (!ctx) return BWTS_B200_EINVAL;
+    ctx->profile = on != 0;
+    return 0;
+}
+extern "C" const char *bwts_b200_strerror(int code)
+{
+    switch (code) {
+    case BWTS_B200_OK: return "ok";
+    case BWTS_B200_EINVAL: return "invalid argument";
+    case BWTS_B200_ETOOBIG: return "input longer than 2^30 bytes per block";
+    case BWTS_B200_ENODEV: return "no usable CUDA device (there is no CPU fallback)";
+    case BWTS_B200_ENOMEM: return "out of device or pinned host memory";
+    case BWTS_B200_ECUDA: return "CUDA error";
+    case BWTS_B200_EINTERNAL: return "internal invariant violated";
+    default: return "unknown error";
+    }
+}
+extern "C" int bwts_b200_last_cuda_error(const bwts_b200_ctx *ctx) { return ctx ? ctx->last_cuda : 0; }
+extern "C" const char *bwts_b200_version(void) { return BWTS_VERSION; }
+extern "C" int bwts_b200_tune(int key, long value)
+{
+    if (key == 0) { if (value < 0) return BWTS_B200_EINVAL; g_tune_chunk = value; return 0; }
+    if (key == 1) { if (value != 0 && (value < 20 || value > 31)) return BWTS_B200_EINVAL; g_tune_spl_shift = value; return 0; }
+    return BWTS_B200_EINVAL;
+}

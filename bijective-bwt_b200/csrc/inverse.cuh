@@ -1,0 +1,343 @@
+// inverse.cuh -- inverse BWTS kernels.
+//
+// Reference: /root/reference/unbwts.c:31-86.  prev[i] = C[B[i]] + occ(B[i], i) is the
+// stable LF map (:31-52); its cycles are the Lyndon factors.  The reference walks them one
+// byte at a time (:62-86): cycles in order of ascending smallest index, the first one
+// landing at the END of the output, bytes of a cycle written at descending positions
+// starting from the cycle's smallest index.  Closed form used here:
+//     out[n-1 - off(c) - d(i)] = B[i]
+// d(i) = prev-steps from the smallest index of i's cycle to i, off(c) = total length of
+// the cycles whose smallest index is below c's.
+//
+// d and off come from list ranking with hashed splitters: every splitter walks its
+// sublist once (k_inv_walk), the reduced list of splitters is ranked by pointer jumping
+// (min, then suffix sums cut at the sublist holding the cycle's minimum), cycles without
+// any splitter are walked directly (k_inv_self_walk), an exclusive scan over the cycle
+// lengths parked at the cycle minima gives off, and k_inv_place scatters the bytes.
+#pragma once
+#include "common.cuh"
+
+#define INV_TILE 8192  // bytes per tile, 256 threads x 32
+#define INV_NT 256
+#define INV_CHUNK 256  // tiles per column-scan chunk
+
+// ---- byte counts per tile -------------------------------------------------------------------
+__global__ void __launch_bounds__(INV_NT) k_inv_tile_hist(const u8 *__restrict__ B, u32 n, u32 *__restrict__ tilehist)
+{
+    __shared__ u32 wh[INV_NT / 32][256];
+    const u32 tid = threadIdx.x, warp = tid >> 5;
+    for (u32 i = tid; i < (INV_NT / 32) * 256; i += INV_NT) ((u32 *)wh)[i] = 0;
+    __syncthreads();
+    const u32 base = blockIdx.x * INV_TILE;
+    u32 *h = wh[warp];
+    // two 16-byte vectors per thread; runs of equal bytes are folded before the atomic
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        const u32 p = base + (v * INV_NT + tid) * 16;
+        if (p + 16 <= n) {
+            const uint4 x = ldg_stream_u4((const uint4 *)(B + p));
+            const u32 w[4] = {x.x, x.y, x.z, x.w};
+            u32 cur = w[0] & 255, run = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int s = 0; s < 32; s += 8) {
+                    const u32 c = (w[q] >> s) & 255;
+                    if (c == cur) run++;
+                    else { atomicAdd(&h[cur], run); cur = c; run = 1; }
+                }
+            atomicAdd(&h[cur], run);
+        } else {
+            for (u32 q = p; q < n && q < p + 16; q++) atomicAdd(&h[B[q]], 1u);
+        }
+    }
+    __syncthreads();
+    u32 s = 0;
+#pragma unroll
+    for (int w = 0; w < INV_NT / 32; w++) s += wh[w][tid];
+    tilehist[(u64)blockIdx.x * 256 + tid] = s;
+}
+
+// column sums over chunks of INV_CHUNK tiles (grid = nchunks, block = 256)
+__global__ void __launch_bounds__(256) k_inv_colsum(const u32 *__restrict__ tilehist, u32 ntiles,
+                                                    u32 *__restrict__ chunksum)
+{
+    const u32 lo = blockIdx.x * INV_CHUNK, hi = min(ntiles, lo + INV_CHUNK);
+    u32 s = 0;
+    for (u32 t = lo; t < hi; t++) s += tilehist[(u64)t * 256 + threadIdx.x];
+    chunksum[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
+// single block: per byte exclusive scan over chunks, then add C[byte]
+__global__ void __launch_bounds__(256) k_inv_chunk_scan(u32 *__restrict__ chunksum, u32 nchunks)
+{
+    __shared__ u32 ws[8];
+    const u32 d = threadIdx.x;
+    u32 run = 0;
+    for (u32 c = 0; c < nchunks; c++) {
+        const u32 v = chunksum[c * 256 + d];
+        chunksum[c * 256 + d] = run;
+        run += v;
+    }
+    const u32 incl = warp_incl_sum(run);
+    if (lane_id() == 31) ws[d >> 5] = incl;
+    __syncthreads();
+    u32 C = incl - run;
+    for (u32 w = 0; w < (d >> 5); w++) C += ws[w];
+    for (u32 c = 0; c < nchunks; c++) chunksum[c * 256 + d] += C;
+}
+
+// tilehist -> exclusive base per (tile, byte), in place
+__global__ void __launch_bounds__(256) k_inv_tile_base(u32 *__restrict__ tilehist, u32 ntiles,
+                                                       const u32 *__restrict__ chunksum)
+{
+    const u32 lo = blockIdx.x * INV_CHUNK, hi = min(ntiles, lo + INV_CHUNK);
+    u32 run = chunksum[blockIdx.x * 256 + threadIdx.x];
+    for (u32 t = lo; t < hi; t++) {
+        const u32 v = tilehist[(u64)t * 256 + threadIdx.x];
+        tilehist[(u64)t * 256 + threadIdx.x] = run;
+        run += v;
+    }
+}
+
+// ---- stable LF map ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(INV_NT) k_inv_lf_rank(const u8 *__restrict__ B, u32 n,
+                                                        const u32 *__restrict__ tilebase, u32 *__restrict__ prev)
+{
+    __shared__ __align__(16) u8 s_b[INV_TILE];
+    __shared__ u32 s_wcnt[INV_NT / 32][256];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 base = blockIdx.x * INV_TILE;
+    for (u32 i = tid; i < (INV_NT / 32) * 256; i += INV_NT) ((u32 *)s_wcnt)[i] = 0;
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        const u32 o = (v * INV_NT + tid) * 16;
+        if (base + o + 16 <= n) {
+            *(uint4 *)(s_b + o) = ldg_stream_u4((const uint4 *)(B + base + o));
+        } else {
+            for (u32 q = 0; q < 16; q++) s_b[o + q] = (base + o + q < n) ? B[base + o + q] : 0;
+        }
+    }
+    __syncthreads();
+    // warp w ranks bytes [w*1024, (w+1)*1024) of the tile, 32 at a time, in order
+    constexpr int ROUNDS = INV_TILE / INV_NT;  // 32
+    const u32 wo = warp * (32 * ROUNDS);
+    u32 *wc = s_wcnt[warp];
+    const u32 lt = lanemask_lt();
+    u16 rnk[ROUNDS];
+#pragma unroll
+    for (int j = 0; j < ROUNDS; j++) {
+        const u32 o = wo + j * 32 + lane;
+        const bool valid = base + o < n;
+        const u32 d = valid ? s_b[o] : 256u + lane;  // invalid lanes match nobody
+        const u32 peers = __match_any_sync(FULL_MASK, d);
+        const int leader = __ffs(peers) - 1;
+        u32 before = 0;
+        if (valid && (int)lane == leader) {
+            before = wc[d];
+            wc[d] = before + __popc(peers);
+        }
+        before = __shfl_sync(FULL_MASK, before, leader);
+        rnk[j] = (u16)(before + __popc(peers & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const u32 d = tid;
+        u32 run = __ldg(tilebase + (u64)blockIdx.x * 256 + d);
+#pragma unroll
+        for (int w = 0; w < INV_NT / 32; w++) {
+            const u32 c = s_wcnt[w][d];
+            s_wcnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ROUNDS; j++) {
+        const u32 o = wo + j * 32 + lane;
+        if (base + o < n) prev[base + o] = wc[s_b[o]] + rnk[j];
+    }
+}
+
+// ---- splitters ------------------------------------------------------------------------------------
+static __device__ __forceinline__ bool is_splitter(u32 i, u32 shift) { return ((i * 0x9E3779B1u) >> shift) == 0; }
+
+#define SP_TILE 4096
+__global__ void __launch_bounds__(256) k_inv_spl_count(u32 n, u32 shift, u32 *__restrict__ tilecnt)
+{
+    __shared__ u32 ws[8];
+    const u32 base = blockIdx.x * SP_TILE + threadIdx.x * 16;
+    u32 c = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) c += (base + q < n) && is_splitter(base + q, shift);
+    c = warp_sum(c);
+    if (lane_id() == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 s = 0;
+        for (int w = 0; w < 8; w++) s += ws[w];
+        tilecnt[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) k_inv_spl_write(u32 n, u32 shift, const u32 *__restrict__ tileoff,
+                                                       u32 *__restrict__ spl, uint2 *__restrict__ rec)
+{
+    __shared__ u32 ws[8];
+    const u32 base = blockIdx.x * SP_TILE + threadIdx.x * 16;
+    u32 c = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) c += (base + q < n) && is_splitter(base + q, shift);
+    const u32 incl = warp_incl_sum(c);
+    if (lane_id() == 31) ws[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 s = tileoff[blockIdx.x] + incl - c;
+    for (u32 w = 0; w < (threadIdx.x >> 5); w++) s += ws[w];
+#pragma unroll
+    for (int q = 0; q < 16; q++)
+        if ((base + q < n) && is_splitter(base + q, shift)) {
+            spl[s] = base + q;
+            rec[base + q] = make_uint2(s, 0u);
+            s++;
+        }
+}
+
+// one thread per splitter: follow prev until the next splitter, label the sublist.
+// rec[i] = (sublist id, offset inside the sublist); jm[s] = next sublist << 32 | smallest index
+__global__ void __launch_bounds__(128) k_inv_walk(const u32 *__restrict__ prev, u32 shift,
+                                                  const u32 *__restrict__ spl, u32 ns, uint2 *__restrict__ rec,
+                                                  u64 *__restrict__ jm, u32 *__restrict__ wlen,
+                                                  uint2 *__restrict__ minfo)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const u32 i0 = spl[s];
+    u32 mn = i0, mo = 0, o = 1;
+    u32 i = prev[i0];
+    while (!is_splitter(i, shift)) {
+        rec[i] = make_uint2(s, o);
+        if (i < mn) { mn = i; mo = o; }
+        i = prev[i];
+        o++;
+    }
+    const u32 nxt = rec[i].x;  // written by k_inv_spl_write
+    jm[s] = ((u64)nxt << 32) | mn;
+    wlen[s] = o;
+    minfo[s] = make_uint2(mn, mo);
+}
+
+// pointer jumping with min: (jmp, mn) <- (jmp[jmp], min(mn, mn[jmp]))
+__global__ void __launch_bounds__(256) k_inv_min_jump(const u64 *__restrict__ in, u64 *__restrict__ out, u32 ns)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const u64 a = in[s];
+    const u64 b = in[(u32)(a >> 32)];
+    out[s] = (b & 0xffffffff00000000ull) | (u64)min((u32)a, (u32)b);
+}
+
+// suffix sums over the reduced list, cut in front of the sublist that holds the cycle minimum.
+// pv[s] = ptr << 32 | val
+__global__ void __launch_bounds__(256) k_inv_sum_init(const u64 *__restrict__ jm0, const u64 *__restrict__ jmR,
+                                                      const u32 *__restrict__ wlen, const uint2 *__restrict__ minfo,
+                                                      u32 ns, u64 *__restrict__ pv)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const u32 nxt = (u32)(jm0[s] >> 32);
+    const u32 cm = (u32)jmR[s];
+    const bool next_is_origin = minfo[nxt].x == cm;
+    pv[s] = ((u64)(next_is_origin ? NONE32 : nxt) << 32) | wlen[s];
+}
+__global__ void __launch_bounds__(256) k_inv_sum_jump(const u64 *__restrict__ in, u64 *__restrict__ out, u32 ns)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    u64 a = in[s];
+    const u32 p = (u32)(a >> 32);
+    if (p != NONE32) {
+        const u64 b = in[p];
+        a = (b & 0xffffffff00000000ull) | (u64)((u32)a + (u32)b);
+    }
+    out[s] = a;
+}
+
+// the sublist holding the cycle minimum publishes the cycle: length at the minimum's index
+// (for the offsets scan) and (length, offset of the minimum inside that sublist)
+__global__ void __launch_bounds__(256) k_inv_origin_publish(const u64 *__restrict__ jmR, const u64 *__restrict__ pvR,
+                                                            const uint2 *__restrict__ minfo, u32 ns,
+                                                            u32 *__restrict__ len_at_min, uint2 *__restrict__ cyc)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const u32 cm = (u32)jmR[s];
+    const uint2 mi = minfo[s];
+    if (mi.x == cm) {
+        const u32 L = (u32)pvR[s];
+        len_at_min[cm] = L;
+        cyc[cm] = make_uint2(L, mi.y);
+    }
+}
+
+// elements no walk reached belong to cycles without a splitter: walk the whole cycle.
+// rec[i] = (0x80000000 | smallest index, d(i))
+__global__ void __launch_bounds__(256) k_inv_self_walk(const u32 *__restrict__ prev, u32 n, uint2 *__restrict__ rec,
+                                                       u32 *__restrict__ len_at_min, u32 *__restrict__ counters)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (rec[i].x != NONE32) return;
+    u32 j = prev[i], steps = 1, mn = i, mstep = 0;
+    while (j != i) {
+        if (j < mn) { mn = j; mstep = steps; }
+        j = prev[j];
+        steps++;
+    }
+    const u32 d = (mstep == 0) ? 0 : steps - mstep;
+    rec[i] = make_uint2(0x80000000u | mn, d);
+    if (mn == i) { len_at_min[i] = steps; atomicAdd(counters + 1, 1u); }
+    atomicAdd(counters + 0, 1u);
+}
+
+// per sublist: (A, L, off) with d(i) = (A + offset(i)) mod L
+__global__ void __launch_bounds__(256) k_inv_spl_record(const u64 *__restrict__ jmR, const u64 *__restrict__ pvR,
+                                                        const uint2 *__restrict__ cyc, const u32 *__restrict__ off,
+                                                        u32 ns, uint4 *__restrict__ srec)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const u32 cm = (u32)jmR[s];
+    const uint2 c = cyc[cm];  // (L, offset of the minimum in the origin sublist)
+    const u32 L = c.x;
+    u32 A = (L - (u32)pvR[s]) + (L - c.y);  // P(s) + L - o(m), both terms in (0, L]
+    while (A >= L) A -= L;
+    srec[s] = make_uint4(A, L, off[cm], 0u);
+}
+
+__global__ void __launch_bounds__(256) k_inv_place(const u8 *__restrict__ B, u32 n, const uint2 *__restrict__ rec,
+                                                   const uint4 *__restrict__ srec, const u32 *__restrict__ off,
+                                                   u8 *__restrict__ out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 r = rec[i];
+    u32 pos;
+    if (r.x & 0x80000000u) {
+        pos = n - 1 - __ldg(off + (r.x & 0x7fffffffu)) - r.y;
+    } else {
+        const uint4 q = __ldg(srec + r.x);
+        u32 d = q.x + r.y;
+        if (d >= q.y) d -= q.y;
+        pos = n - 1 - q.z - d;
+    }
+    out[pos] = B[i];
+}
+
+// count cycles: entries of len_at_min that are non-zero
+__global__ void __launch_bounds__(256) k_inv_count_cycles(const u32 *__restrict__ len_at_min, u32 n, u32 *__restrict__ counter)
+{
+    u32 c = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += len_at_min[i] != 0;
+    c = warp_sum(c);
+    if (lane_id() == 0 && c) atomicAdd(counter, c);
+}

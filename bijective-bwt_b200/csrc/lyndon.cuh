@@ -1,0 +1,254 @@
+// lyndon.cuh -- parallel Lyndon-boundary kernels.
+//
+// The reference finds factor starts as the strict prefix minima of the inverse suffix
+// array (/root/reference/mk_bwts_sa.c:126-129), i.e. position i starts a factor iff the
+// suffix T[i..n) is smaller than every earlier suffix.  Here, with no suffix array:
+//   1. k_duval_chunks   one thread per chunk [b,e) runs Duval's algorithm on the suffix
+//                       T[b..n) until the pending factor starts at or after e.  That marks
+//                       exactly the positions of the chunk that are smaller than every
+//                       earlier suffix *starting in the same chunk* (a decreasing list).
+//   2. k_chunkmin_*     exclusive prefix minimum, in suffix order, of the chunks' last
+//                       marks (= each chunk's smallest suffix).
+//   3. k_chunk_threshold a mark survives iff its suffix is below that minimum; survivors
+//                       are a tail of the chunk's list (binary search, warp-wide compares).
+#pragma once
+#include "common.cuh"
+
+#define LY_GROUP 32  // chunks per warp in the min-scan kernels
+
+// T[a..n) < T[b..n) for a != b; whole warp cooperates (uniform arguments and result).
+static __device__ __forceinline__ bool suffix_less_warp(const u8 *__restrict__ T, u32 n, u32 a, u32 b)
+{
+    const u32 lane = lane_id();
+    u32 off = 0;
+    for (;;) {
+        const u32 pa = a + off + lane * 8, pb = b + off + lane * 8;
+        bool diff = true;  // lanes too close to the end defer to the byte loop
+        if ((u64)pa + 16 <= n && (u64)pb + 16 <= n) diff = load8_unaligned(T + pa) != load8_unaligned(T + pb);
+        const u32 mask = __ballot_sync(FULL_MASK, diff);
+        if (mask == 0) { off += 256; continue; }
+        const u32 l = __ffs(mask) - 1;
+        u32 p = a + off + l * 8, q = b + off + l * 8;
+        while (p < n && q < n) {
+            const u8 ca = T[p], cb = T[q];
+            if (ca != cb) return ca < cb;
+            p++; q++;
+        }
+        return p >= n;  // the suffix that ends first is the smaller one
+    }
+}
+
+// ---- 1. Duval per chunk -----------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_duval_chunks(const u8 *__restrict__ T, u32 n, u32 chunk, u32 nch,
+                                                      u8 *__restrict__ flags, u32 *__restrict__ chunk_last)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nch) return;
+    const u32 b = t * chunk;
+    const u32 e = min(n, b + chunk);
+    u32 f = b, last = b;
+    while (f < e) {
+        u32 i = f, k = f + 1;
+        while (k < n) {
+            const u8 ci = T[i], ck = T[k];
+            if (ci > ck) break;
+            if (ci < ck) { i = f; k++; continue; }
+            i++; k++;
+            // inside a periodic stretch: skip 8 bytes at a time (i < k)
+            while ((u64)k + 16 <= n && load8_unaligned(T + i) == load8_unaligned(T + k)) { i += 8; k += 8; }
+        }
+        const u32 p = k - i;
+        while (f <= i && f < e) {
+            flags[f] = 1;
+            last = f;
+            f += p;
+        }
+        if (f <= i) f = e;  // the remaining copies start beyond this chunk
+    }
+    chunk_last[t] = last;
+}
+
+// ---- 2. exclusive prefix minimum of chunk_last in suffix order ---------------------------
+static __device__ __forceinline__ u32 suffix_min_warp(const u8 *T, u32 n, u32 a, u32 b)
+{
+    if (a == NONE32) return b;
+    if (b == NONE32) return a;
+    return suffix_less_warp(T, n, b, a) ? b : a;
+}
+
+// one warp per group of LY_GROUP chunks
+__global__ void __launch_bounds__(128) k_chunkmin_reduce(const u8 *__restrict__ T, u32 n,
+                                                         const u32 *__restrict__ chunk_last, u32 nch,
+                                                         u32 *__restrict__ group_min, u32 ngroups)
+{
+    const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= ngroups) return;
+    const u32 lo = g * LY_GROUP, hi = min(nch, lo + LY_GROUP);
+    u32 run = NONE32;
+    for (u32 t = lo; t < hi; t++) run = suffix_min_warp(T, n, run, chunk_last[t]);
+    if (lane_id() == 0) group_min[g] = run;
+}
+
+// single block of 32 warps: exclusive scan of group_min -> group_excl
+__global__ void __launch_bounds__(1024) k_chunkmin_scan(const u8 *__restrict__ T, u32 n,
+                                                        const u32 *__restrict__ group_min, u32 ngroups,
+                                                        u32 *__restrict__ group_excl)
+{
+    __shared__ u32 part[32];
+    const u32 warp = threadIdx.x >> 5, lane = lane_id();
+    const u32 per = (ngroups + 31) / 32;
+    const u32 lo = min(ngroups, warp * per), hi = min(ngroups, lo + per);
+    u32 run = NONE32;
+    for (u32 g = lo; g < hi; g++) run = suffix_min_warp(T, n, run, group_min[g]);
+    if (lane == 0) part[warp] = run;
+    __syncthreads();
+    if (warp == 0) {
+        u32 acc = NONE32;
+        for (u32 w = 0; w < 32; w++) {
+            const u32 mine = part[w];
+            __syncwarp();
+            if (lane == 0) part[w] = acc;
+            acc = suffix_min_warp(T, n, acc, mine);
+        }
+    }
+    __syncthreads();
+    run = part[warp];
+    for (u32 g = lo; g < hi; g++) {
+        if (lane == 0) group_excl[g] = run;
+        run = suffix_min_warp(T, n, run, group_min[g]);
+    }
+}
+
+// ---- 3. per chunk: drop the marks that are not below the minimum of everything before ----
+// position of the j-th (0-based) mark in [b,e); every lane owns a contiguous slice.
+static __device__ u32 select_mark_warp(const u8 *flags, u32 b, u32 e, u32 j)
+{
+    const u32 lane = lane_id();
+    const u32 len = e - b, per = (len + 31) / 32;
+    const u32 lo = min(e, b + lane * per), hi = min(e, lo + per);
+    u32 c = 0;
+    for (u32 p = lo; p < hi; p++) c += flags[p];
+    const u32 incl = warp_incl_sum(c), excl = incl - c;
+    const u32 owner = __ffs(__ballot_sync(FULL_MASK, j < incl)) - 1;
+    u32 pos = NONE32;
+    if (lane == owner) {
+        u32 need = j - excl;
+        for (u32 p = lo; p < hi; p++)
+            if (flags[p]) { if (need == 0) { pos = p; break; } need--; }
+    }
+    return __shfl_sync(FULL_MASK, pos, owner);
+}
+
+static __device__ void clear_flags_warp(u8 *flags, u32 lo, u32 hi)
+{
+    for (u32 p = lo + lane_id(); p < hi; p += 32) flags[p] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_chunk_threshold(const u8 *__restrict__ T, u32 n, u32 chunk, u32 nch,
+                                                         u8 *__restrict__ flags, const u32 *__restrict__ chunk_last,
+                                                         const u32 *__restrict__ group_excl, u32 ngroups)
+{
+    const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= ngroups) return;
+    const u32 lo = g * LY_GROUP, hi = min(nch, lo + LY_GROUP);
+    u32 run = group_excl[g];
+    for (u32 t = lo; t < hi; t++) {
+        const u32 mlast = chunk_last[t];
+        if (run != NONE32) {
+            const u32 b = t * chunk, e = min(n, b + chunk);
+            if (!suffix_less_warp(T, n, mlast, run)) {
+                clear_flags_warp(flags, b, e);  // nothing in this chunk beats the earlier minimum
+            } else if (!suffix_less_warp(T, n, b, run)) {
+                // marks are decreasing in suffix order: first (=b) fails, last succeeds
+                u32 c = 0;
+                {
+                    const u32 per = (e - b + 31) / 32;
+                    const u32 l0 = min(e, b + lane_id() * per), h0 = min(e, l0 + per);
+                    for (u32 p = l0; p < h0; p++) c += flags[p];
+                    c = warp_sum(c);
+                }
+                u32 a = 0, z = c - 1;  // invariant: mark a fails, mark z succeeds
+                u32 zpos = mlast;
+                while (z - a > 1) {
+                    const u32 mid = (a + z) >> 1;
+                    const u32 pos = select_mark_warp(flags, b, e, mid);
+                    if (suffix_less_warp(T, n, pos, run)) { z = mid; zpos = pos; } else a = mid;
+                }
+                clear_flags_warp(flags, b, zpos);
+            }
+            __syncwarp();
+        }
+        run = suffix_min_warp(T, n, run, mlast);
+    }
+}
+
+// ---- factor table ------------------------------------------------------------------------
+// tile = 4096 flags per block of 256 threads (16 bytes per thread)
+#define FL_TILE 4096
+__global__ void __launch_bounds__(256) k_flag_count(const u8 *__restrict__ flags, u32 n, u32 *__restrict__ tile_cnt)
+{
+    __shared__ u32 ws[8];
+    const u32 base = blockIdx.x * FL_TILE + threadIdx.x * 16;
+    u32 c = 0;
+    if (base + 16 <= n) {
+        const uint4 v = *(const uint4 *)(flags + base);
+        c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);  // flags are 0/1 bytes
+    } else {
+        for (u32 p = base; p < n; p++) c += flags[p];
+    }
+    c = warp_sum(c);
+    if (lane_id() == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 s = 0;
+        for (int w = 0; w < 8; w++) s += ws[w];
+        tile_cnt[blockIdx.x] = s;
+    }
+}
+
+// tile_off = exclusive scan of tile_cnt.  Writes FS[rank] = position for every mark.
+__global__ void __launch_bounds__(256) k_flag_write(const u8 *__restrict__ flags, u32 n,
+                                                    const u32 *__restrict__ tile_off, u32 *__restrict__ FS)
+{
+    __shared__ u32 ws[8];
+    const u32 base = blockIdx.x * FL_TILE + threadIdx.x * 16;
+    u8 loc[16];
+    u32 c = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        loc[q] = (base + q < n) ? flags[base + q] : 0;
+        c += loc[q];
+    }
+    const u32 incl = warp_incl_sum(c);
+    if (lane_id() == 31) ws[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 off = tile_off[blockIdx.x] + incl - c;
+    for (u32 w = 0; w < (threadIdx.x >> 5); w++) off += ws[w];
+#pragma unroll
+    for (int q = 0; q < 16; q++)
+        if (loc[q]) FS[off++] = base + q;
+}
+
+// longest factor + coarse index.  FS[F] = n must already be in place.
+__global__ void k_factor_lmax(const u32 *__restrict__ FS, u32 F, u32 *__restrict__ lmax)
+{
+    u32 best = 0;
+    for (u32 f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x)
+        best = max(best, FS[f + 1] - FS[f]);
+    best = warp_max(best);
+    if (lane_id() == 0 && best) atomicMax(lmax, best);
+}
+
+__global__ void k_coarse_index(const u32 *__restrict__ FS, u32 F, u32 *__restrict__ cidx, u32 nblk)
+{
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblk) return;
+    if (b == nblk) { cidx[b] = F - 1; return; }
+    const u32 pos = b << COARSE_BITS;
+    u32 lo = 0, hi = F - 1;  // largest f with FS[f] <= pos
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (FS[mid] <= pos) lo = mid; else hi = mid - 1;
+    }
+    cidx[b] = lo;
+}

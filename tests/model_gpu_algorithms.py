@@ -1,0 +1,266 @@
+"""Executable specification (numpy / pure Python) of the PARALLEL algorithms the CUDA
+kernels implement, kernel by kernel.  It exists so the maths can be checked against the
+oracle on a CPU-only box; it is test code, not a product path (the product has no CPU
+fallback and never imports this).
+
+forward:  chunked Lyndon boundaries -> packed initial keys -> prefix doubling over the
+          cyclic successor map with a shrinking live set -> emit
+inverse:  stable LF map -> hashed splitters + sublist walks -> reduced-list min / sum
+          jumping -> cycle offsets scan -> placement
+"""
+import numpy as np
+
+
+# --------------------------------------------------------------------------- forward
+
+def suffix_less(T, a, b):
+    """T[a:] < T[b:] (a != b); the shorter suffix wins a tie."""
+    n = len(T)
+    while a < n and b < n:
+        if T[a] != T[b]:
+            return T[a] < T[b]
+        a += 1
+        b += 1
+    return a == n  # a ran out first => a is the shorter => smaller
+
+
+def lyndon_starts_chunked(T, B):
+    """lyndon.cu: k_duval_chunks + k_chunk_min_scan + k_chunk_threshold."""
+    n = len(T)
+    flags = np.zeros(n, dtype=np.uint8)
+    nch = (n + B - 1) // B
+    last = np.zeros(nch, dtype=np.int64)
+    # K1: every chunk runs Duval on the suffix T[b:], until the pending factor starts
+    # at or beyond the chunk end; marks factor starts inside the chunk.
+    for t in range(nch):
+        b, e = t * B, min((t + 1) * B, n)
+        f = b
+        while f < e:
+            i, k = f, f + 1
+            while k < n and T[i] <= T[k]:
+                i = f if T[i] < T[k] else i + 1
+                k += 1
+            p = k - i
+            while f <= i and f < e:
+                flags[f] = 1
+                last[t] = f
+                f += p
+            if f <= i:  # remaining copies start beyond the chunk
+                f = e
+    # K2: exclusive prefix minimum (suffix order) of the per-chunk minima
+    M = np.full(nch, -1, dtype=np.int64)
+    run = -1
+    for t in range(nch):
+        M[t] = run
+        if run < 0 or suffix_less(T, last[t], run):
+            run = last[t]
+    # K3: in each chunk the marked starts are decreasing in suffix order; keep the
+    # suffix of that list that is below the minimum of everything before the chunk.
+    for t in range(1, nch):
+        b, e = t * B, min((t + 1) * B, n)
+        cand = [p for p in range(b, e) if flags[p]]
+        lo, hi = 0, len(cand)          # first index whose suffix < T[M[t]:]
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if suffix_less(T, cand[mid], M[t]):
+                hi = mid
+            else:
+                lo = mid + 1
+        for p in cand[:lo]:
+            flags[p] = 0
+    return np.flatnonzero(flags)
+
+
+def forward(T, chunk=16, trace=None):
+    T = np.frombuffer(bytes(T), dtype=np.uint8)
+    n = len(T)
+    FS = np.append(lyndon_starts_chunked(T, chunk), n).astype(np.int64)
+    fid = np.searchsorted(FS, np.arange(n), side="right") - 1
+    fs, fl = FS[fid], FS[fid + 1] - FS[fid]
+    lmax = int(fl.max())
+
+    def succ_k(i, k):
+        return fs[i] + (i - fs[i] + k) % fl[i]
+
+    # alphabet compaction + packed initial key of k0 symbols (forward.cu: k_init_keys)
+    present = np.zeros(256, dtype=bool)
+    present[T] = True
+    code = np.cumsum(present) - 1
+    sigma = int(present.sum())
+    bits = max(1, int(np.ceil(np.log2(sigma)))) if sigma > 1 else 1
+    k0 = 64 // bits
+    pos = np.arange(n)
+    key = np.zeros(n, dtype=object)
+    for _ in range(k0):
+        key = key * (1 << bits) + code[T[pos]]
+        pos = succ_k(pos, 1)
+    order = np.array(sorted(range(n), key=lambda i: key[i]), dtype=np.int64)
+    skey = key[order]
+
+    rank = np.zeros(n, dtype=np.int64)
+    # live arrays
+    idx = order.copy()
+    grp = np.zeros(n, dtype=np.int64)   # global rank of the group head, by live position
+    gst = np.zeros(n, dtype=np.int64)   # live-array offset of the group start
+    m = n
+    k = k0
+    rounds = 0
+
+    def rerank(skey, idx, grp, gst, m, finalize=False):
+        j = np.arange(m)
+        head = (j == gst[:m])
+        if finalize:
+            head[:] = True
+        else:
+            head[1:] |= np.array([skey[a] != skey[a - 1] for a in range(1, m)], dtype=bool)
+        nxt = np.append(head[1:], True)
+        keep = ~(head & nxt)
+        jh = np.maximum.accumulate(np.where(head, j, -1))
+        newrank = grp[:m] + (jh - gst[:m])
+        changed = newrank != grp[:m]
+        rank[idx[:m][changed]] = newrank[changed]
+        c = np.cumsum(keep) - keep       # exclusive
+        nidx = idx[:m][keep]
+        ngrp = newrank[keep]
+        ngst = (c - (j - jh))[keep]
+        nheads = int(head.sum())
+        return nidx, ngrp, ngst, int(keep.sum()), nheads
+
+    old_groups = 1
+    nidx, ngrp, ngst, m2, nheads = rerank(skey, idx, grp, gst, m)
+    idx, grp, gst, m = nidx, ngrp, ngst, m2
+    while m > 0 and k < 2 * lmax:
+        groups_before = int((gst[:m] == np.arange(m)).sum())
+        key2 = rank[succ_k(idx[:m], k)]
+        comp = gst[:m] * (n + 1) + key2
+        perm = np.argsort(comp, kind="stable")
+        skey = comp[perm]
+        idx = idx[:m][perm]
+        nidx, ngrp, ngst, m2, nheads = rerank(skey, idx, grp, gst, m)
+        rounds += 1
+        k *= 2
+        if nheads == groups_before:     # fixpoint: nothing split
+            break
+        idx, grp, gst, m = nidx, ngrp, ngst, m2
+    if m > 0:
+        rerank(None, idx, grp, gst, m, finalize=True)
+    if trace is not None:
+        trace.update(rounds=rounds, k=k, factors=len(FS) - 1, bits=bits, k0=k0)
+    # emit (forward.cu: k_emit / k_emit_heads)
+    out = np.zeros(n, dtype=np.uint8)
+    prevpos = np.arange(n) - 1
+    isstart = np.zeros(n, dtype=bool)
+    isstart[FS[:-1]] = True
+    prevpos[isstart] = FS[fid[isstart] + 1] - 1
+    out[rank] = T[prevpos]
+    assert len(np.unique(rank)) == n
+    return out.tobytes()
+
+
+# --------------------------------------------------------------------------- inverse
+
+def is_splitter(i, shift=26):
+    return ((np.uint64(i) * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF)) >> np.uint64(shift) == 0
+
+
+def inverse(Bs, shift=26):
+    B = np.frombuffer(bytes(Bs), dtype=np.uint8)
+    n = len(B)
+    # LF map (inverse.cu: k_tile_hist, k_scan_*, k_lf_rank)
+    cnt = np.bincount(B, minlength=256)
+    C = np.cumsum(cnt) - cnt
+    prev = np.zeros(n, dtype=np.int64)
+    seen = np.zeros(256, dtype=np.int64)
+    for i in range(n):
+        prev[i] = C[B[i]] + seen[B[i]]
+        seen[B[i]] += 1
+    # splitters (k_splitter_*)
+    spl = np.array([i for i in range(n) if is_splitter(i, shift)], dtype=np.int64)
+    ns = len(spl)
+    NONE = -1
+    rec_head = np.full(n, NONE, dtype=np.int64)
+    rec_off = np.zeros(n, dtype=np.int64)
+    direct = np.zeros(n, dtype=bool)
+    rec_head[spl] = np.arange(ns)
+    nxt = np.zeros(ns, dtype=np.int64)
+    w = np.zeros(ns, dtype=np.int64)
+    mnv = np.zeros(ns, dtype=np.int64)
+    mno = np.zeros(ns, dtype=np.int64)
+    # walk (k_walk)
+    for s in range(ns):
+        i0 = spl[s]
+        mn, mo, o = i0, 0, 1
+        i = prev[i0]
+        while not is_splitter(int(i), shift):
+            rec_head[i], rec_off[i] = s, o
+            if i < mn:
+                mn, mo = i, o
+            i = prev[i]
+            o += 1
+        nxt[s], w[s], mnv[s], mno[s] = rec_head[i], o, mn, mo
+    # min jumping on the reduced list (k_min_jump)
+    jmp, cm = nxt.copy(), mnv.copy()
+    r = 0
+    while (1 << r) < max(ns, 1):
+        cm = np.minimum(cm, cm[jmp]) if ns else cm
+        jmp = jmp[jmp] if ns else jmp
+        r += 1
+    if ns:
+        cm = np.minimum(cm, cm[jmp])
+    origin = mnv == cm
+    # suffix sums with the origin as list terminal (k_sum_jump)
+    ptr = np.where(origin[nxt], -1, nxt) if ns else nxt
+    val = w.copy()
+    for _ in range(r + 1):
+        has = ptr >= 0
+        val = np.where(has, val + val[np.where(has, ptr, 0)], val)
+        ptr = np.where(has, ptr[np.where(has, ptr, 0)], -1)
+    D = val
+    lenAtMin = np.zeros(n, dtype=np.int64)
+    cycL = np.zeros(n, dtype=np.int64)
+    cycO = np.zeros(n, dtype=np.int64)
+    for s in range(ns):
+        if origin[s]:
+            lenAtMin[cm[s]] = D[s]
+            cycL[cm[s]] = D[s]
+            cycO[cm[s]] = mno[s]
+    # fallback: elements no walk reached (k_self_walk)
+    dir_m = np.zeros(n, dtype=np.int64)
+    dir_d = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        if rec_head[i] == NONE:
+            j, steps, mn, mstep = prev[i], 1, i, 0
+            while j != i:
+                if j < mn:
+                    mn, mstep = j, steps
+                j = prev[j]
+                steps += 1
+            L = steps
+            direct[i] = True
+            dir_m[i], dir_d[i] = mn, (L - mstep) % L
+            if mn == i:
+                lenAtMin[i] = L
+    off = np.cumsum(lenAtMin) - lenAtMin
+    # per-splitter record (k_splitter_record)
+    A = np.zeros(ns, dtype=np.int64)
+    Ls = np.zeros(ns, dtype=np.int64)
+    offs = np.zeros(ns, dtype=np.int64)
+    for s in range(ns):
+        L = cycL[cm[s]]
+        P = L - D[s]
+        A[s] = (P - cycO[cm[s]]) % L
+        Ls[s] = L
+        offs[s] = off[cm[s]]
+    # placement (k_place)
+    out = np.zeros(n, dtype=np.uint8)
+    for i in range(n):
+        if direct[i]:
+            pos = n - 1 - off[dir_m[i]] - dir_d[i]
+        else:
+            s = rec_head[i]
+            d = A[s] + rec_off[i]
+            if d >= Ls[s]:
+                d -= Ls[s]
+            pos = n - 1 - offs[s] - d
+        out[pos] = B[i]
+    return out.tobytes()

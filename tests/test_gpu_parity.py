@@ -1,0 +1,209 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle and the
+golden vectors made by the unmodified reference.  Bit-exact (bytes and 32-bit indices;
+there is no floating point on this path).  Run on a B200: python -m pytest tests -m gpu
+"""
+import json
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "vectors.json").read_text())
+
+
+def golden_input(v, gen):
+    if "input" in v:
+        return bytes.fromhex(v["input"])
+    spec = v["spec"]
+    if "kind" in spec:
+        data = gen.make(spec["kind"], spec["seed"], spec["n"])
+    else:
+        data = helpers.families(spec["n"])[spec["family"]]
+    assert helpers.sha256(data) == v["input_sha256"]
+    return data
+
+
+@pytest.fixture(scope="module")
+def ctx(bwts):
+    assert bwts.device_count() >= 1, "no CUDA device: the product has no CPU path"
+    c = bwts.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(autouse=True)
+def default_tuning(bwts):
+    bwts.tune(0, 0)
+    bwts.tune(1, 0)
+    yield
+    bwts.tune(0, 0)
+    bwts.tune(1, 0)
+
+
+def test_golden_vectors_forward_and_inverse(bwts, ctx, gen):
+    """every vector produced by the reference's own mk_bwts / unbwts binaries"""
+    for v in GOLDEN:
+        x = golden_input(v, gen)
+        fwd = ctx.forward_host(x)
+        inv = ctx.inverse_host(x)
+        if "fwd" in v:
+            assert fwd == bytes.fromhex(v["fwd"]), v["name"]
+            assert inv == bytes.fromhex(v["inv"]), v["name"]
+        else:
+            assert helpers.sha256(fwd) == v["fwd_sha256"], v["name"]
+            assert helpers.sha256(inv) == v["inv_sha256"], v["name"]
+
+
+@pytest.mark.parametrize("chunk,shift", [(1, 31), (7, 30), (64, 28), (0, 0)])
+def test_golden_small_with_tiny_chunks(bwts, ctx, gen, chunk, shift):
+    """same vectors with the Lyndon chunk and splitter density forced small, so that inputs
+    of a few bytes already cross chunk / sublist boundaries"""
+    bwts.tune(0, chunk)
+    bwts.tune(1, shift)
+    for v in GOLDEN:
+        if v["n"] > 70_000:
+            continue
+        x = golden_input(v, gen)
+        fwd = ctx.forward_host(x)
+        inv = ctx.inverse_host(x)
+        if "fwd" in v:
+            assert fwd == bytes.fromhex(v["fwd"]), v["name"]
+            assert inv == bytes.fromhex(v["inv"]), v["name"]
+        else:
+            assert helpers.sha256(fwd) == v["fwd_sha256"], v["name"]
+            assert helpers.sha256(inv) == v["inv_sha256"], v["name"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 2047, 2048, 2049, 4095, 4096, 4097, 8191, 8192, 8193,
+                               65535, 65536, 65537])
+def test_families_at_tile_edges(bwts, ctx, oracle, n):
+    bwts.tune(0, 512)
+    bwts.tune(1, 29)
+    for name, x in helpers.families(n).items():
+        assert ctx.forward_host(x) == oracle.forward(x), (name, n)
+        assert ctx.inverse_host(x) == oracle.inverse(x), (name, n)
+
+
+def test_random_small_against_oracle(bwts, ctx, oracle):
+    rng = np.random.default_rng(123)
+    bwts.tune(0, 16)
+    bwts.tune(1, 30)
+    for _ in range(300):
+        n = int(rng.integers(1, 3000))
+        sigma = int(rng.choice([1, 2, 3, 4, 16, 256]))
+        x = rng.integers(0, sigma, size=n, dtype=np.uint8).tobytes()
+        assert ctx.forward_host(x) == oracle.forward(x), x[:64]
+        assert ctx.inverse_host(x) == oracle.inverse(x), x[:64]
+
+
+@pytest.mark.parametrize("kind,seed,n", [("random", 11, 1 << 20), ("text", 12, (1 << 22) + 12345),
+                                         ("tiled", 13, 5 << 20), ("dna", 14, (1 << 23) - 1),
+                                         ("fibonacci", 0, 3_000_001)])
+def test_generated_medium_against_oracle(ctx, oracle, gen, kind, seed, n):
+    x = gen.make(kind, seed, n)
+    y = ctx.forward_host(x)
+    assert y == oracle.forward(x)
+    assert ctx.inverse_host(y) == x
+    assert ctx.inverse_host(x) == oracle.inverse(x)
+
+
+def test_adversarial_one_mib(bwts, ctx, oracle):
+    n = 1 << 20
+    for name, x in helpers.families(n).items():
+        y = ctx.forward_host(x)
+        assert y == oracle.forward(x), name
+        assert ctx.inverse_host(y) == x, name
+
+
+def test_full_size_properties_64mib(ctx, gen):
+    """BASELINE configs[1] at full size: size-independent properties (the oracle comparison
+    at this size lives in bench.py's cpu_baseline sample)"""
+    n = 64 << 20
+    x = gen.make("text", 2, n)
+    y = ctx.forward_host(x)
+    assert len(y) == n and y[0] == x[-1]
+    assert np.array_equal(np.bincount(np.frombuffer(x, np.uint8), minlength=256),
+                          np.bincount(np.frombuffer(y, np.uint8), minlength=256))
+    assert ctx.inverse_host(y) == x
+    # bijectivity the other way round: forward(inverse(x)) == x for an arbitrary string
+    assert ctx.forward_host(ctx.inverse_host(x)) == x
+
+
+def test_oracle_sample_16mib(ctx, oracle, gen):
+    x = gen.make("text", 2, 16 << 20)
+    assert ctx.forward_host(x) == oracle.forward(x)
+
+
+def test_blocks_equal_concatenated_single_blocks(bwts, oracle, gen):
+    x = gen.make("text", 21, 3_000_000)
+    b = 1 << 20
+    want = b"".join(oracle.forward(x[o:o + b]) for o in range(0, len(x), b))
+    ndev = min(2, bwts.device_count())
+    got = bwts.forward_blocks(x, b, devices=list(range(ndev)))
+    assert got == want
+    assert bwts.inverse_blocks(got, b, devices=list(range(ndev))) == x
+    # block_len <= 0 means the reference's behaviour: one block
+    assert bwts.forward_blocks(x, 0) == oracle.forward(x)
+
+
+def test_one_call_entry_points_and_errors(bwts, oracle):
+    x = b"abracadabra" * 1000
+    assert bwts.forward(x) == oracle.forward(x)
+    assert bwts.inverse(x) == oracle.inverse(x)
+    L = bwts.lib()
+    buf = np.zeros(8, dtype=np.uint8)
+    assert L.bwts_b200_forward(None, 8, buf.ctypes.data, 0) == -1
+    assert L.bwts_b200_forward(buf.ctypes.data, 0, buf.ctypes.data, 0) == -1
+    assert L.bwts_b200_forward(buf.ctypes.data, 8, buf.ctypes.data, 999) == -1
+    assert L.bwts_b200_inverse(buf.ctypes.data, (1 << 30) + 1, buf.ctypes.data, 0) == -2
+
+
+def test_device_resident_api_with_torch(bwts, ctx, oracle, gen):
+    import torch
+    x = gen.make("dna", 31, 2_000_000)
+    dev = torch.device("cuda:0")
+    d_in = torch.frombuffer(bytearray(x), dtype=torch.uint8).to(dev)
+    d_out = torch.empty_like(d_in)
+    d_back = torch.empty_like(d_in)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ctx.forward_device(d_in.data_ptr(), len(x), d_out.data_ptr(), stream)
+    ctx.inverse_device(d_out.data_ptr(), len(x), d_back.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert bytes(d_out.cpu().numpy()) == oracle.forward(x)
+    assert bytes(d_back.cpu().numpy()) == x
+    st = ctx.stats()
+    assert st["launches"] > 0 and st["direction"] == 1
+
+
+def test_suffix_array_seam(bwts, oracle, gen):
+    for x in (b"banana", b"mississippi", b"a" * 1000, gen.make("text", 5, 200_000), gen.make("dna", 6, 300_000),
+              helpers.fibonacci_word(50_000)):
+        assert np.array_equal(bwts.suffix_array(x), oracle.suffix_array(x))
+
+
+def test_cli_tools_match_reference_layout(oracle, gen, tmp_path):
+    bindir = helpers.PKG / "bin"
+    x = gen.make("text", 41, 500_000)
+    src = tmp_path / "in.txt"
+    src.write_bytes(x)
+    out = subprocess.run([str(bindir / "mk_bwts"), str(src)], capture_output=True, check=True).stdout
+    assert out == oracle.forward(x)  # stdout default
+    dst = tmp_path / "out.bwts"
+    subprocess.run([str(bindir / "mbwt_new"), str(src), str(dst)], check=True)
+    assert dst.read_bytes() == oracle.forward(x)
+    back = tmp_path / "back.txt"
+    subprocess.run([str(bindir / "unbwts"), str(dst), str(back)], check=True)
+    assert back.read_bytes() == x
+    r = subprocess.run([str(bindir / "unbwts"), str(dst)], capture_output=True, check=True, cwd=tmp_path)
+    assert r.stdout.startswith(b"Writing to ")
+    name = r.stdout.decode().split("Writing to ", 1)[1].strip()
+    assert name.startswith(str(dst) + "_") and Path(name).read_bytes() == x
+    env = dict(os.environ, BWTS_B200_BLOCK="131072")
+    out = subprocess.run([str(bindir / "mk_bwts"), str(src)], capture_output=True, check=True, env=env).stdout
+    assert out == b"".join(oracle.forward(x[o:o + 131072]) for o in range(0, len(x), 131072))
