@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -33,6 +34,7 @@ static const char *kclass_names[BWTS_B200_NCLASS] = {
     "lyndon", "factor_table", "init_keys", "radix_hist", "onesweep_pass", "build_keys", "rerank", "emit",
     "inv_tile_hist", "inv_lf_rank", "inv_walk", "inv_jump", "inv_scan", "inv_place", "misc", "copy"};
 
+static std::atomic<u32> g_epoch{0};  // onesweep status epoch, unique per pass across all contexts
 static long g_tune_chunk = 0;      // Lyndon chunk bytes (0 = auto)
 static long g_tune_spl_shift = 0;  // splitter shift   (0 = 26)
 
@@ -120,6 +122,8 @@ static int arena_reserve(bwts_b200_ctx *ctx, size_t bytes)
     if (bytes <= ctx->arena_bytes) return 0;
     if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
     CK(cudaMalloc((void **)&ctx->arena, bytes));
+    CK(cudaMemset(ctx->arena, 0, bytes));
+    CK(cudaDeviceSynchronize());  // the legacy-stream memset does not order against non-blocking streams
     ctx->arena_bytes = bytes;
     return 0;
 }
@@ -171,8 +175,7 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
     for (int p = 0; p < passes; p++) {
         const int a = sb.cur, b = sb.cur ^ 1;
         const bool ident = identity_vals && p == 0;
-        ctx->epoch = (ctx->epoch + 1) & 0x3fffffffu;
-        if (ctx->epoch == 0) ctx->epoch = 1;
+        do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
         LAUNCH(KC_ONESWEEP, (ident ? 20.0 : 24.0) * m, k_onesweep_pass, tiles, OS_NT, sb.k[a],
                ident ? (const u32 *)nullptr : sb.v[a], sb.k[b], sb.v[b], m, (u32)(p * RADIX_BITS),
                sb.hist + p * RADIX_BINS, sb.status, tickets + p, ctx->epoch);
@@ -219,6 +222,10 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     RerankCounters *rrc = (RerankCounters *)(small + 16);
 
     CK(cudaMemsetAsync(small, 0, 1024 * sizeof(u32), st));
+    // The arena is re-laid-out per call, so the look-back status region may hold stale keys
+    // whose high bits look like a live epoch: clear it once per transform (0.5 B / element);
+    // from here on the per-pass epoch keeps the passes apart without further clearing.
+    CK(cudaMemsetAsync(sb.status, 0, (size_t)os_tiles * RADIX_BINS * sizeof(u64), st));
     u32 F = 1, lmax = n;
 
     if (!linear) {
@@ -227,16 +234,21 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         const u32 nch = cdiv(n, chunk), ngroups = cdiv(nch, LY_GROUP);
         u32 *chunk_last = arena_take<u32>(ctx, nch);
         u32 *group_min = arena_take<u32>(ctx, ngroups);
-        u32 *group_excl = arena_take<u32>(ctx, ngroups);
-        if (!chunk_last || !group_min || !group_excl) return BWTS_B200_EINTERNAL;
+        u32 *group_alt = arena_take<u32>(ctx, ngroups);
+        if (!chunk_last || !group_min || !group_alt) return BWTS_B200_EINTERNAL;
         CK(cudaMemsetAsync(flags, 0, n, st));
         LAUNCH(KC_LYNDON, 2.0 * n, k_duval_chunks, cdiv(nch, 128), 128, dT, n, chunk, nch, flags, chunk_last);
         if (nch > 1) {
             LAUNCH(KC_LYNDON, 0, k_chunkmin_reduce, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk_last, nch,
                    group_min, ngroups);
-            LAUNCH(KC_LYNDON, 0, k_chunkmin_scan, 1, 1024, dT, n, group_min, ngroups, group_excl);
+            u32 *gin = group_min, *gout = group_alt;
+            for (u32 stride = 1; stride < ngroups; stride <<= 1) {
+                LAUNCH(KC_LYNDON, 0, k_chunkmin_level, cdiv((u64)ngroups * 32, 128), 128, dT, n, gin, gout, ngroups,
+                       stride);
+                u32 *t = gin; gin = gout; gout = t;
+            }
             LAUNCH(KC_LYNDON, 0, k_chunk_threshold, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk, nch, flags,
-                   chunk_last, group_excl, ngroups);
+                   chunk_last, gin, ngroups);
         }
         // -- factor table
         LAUNCH(KC_FACTORS, 1.0 * n, k_flag_count, ntl, 256, flags, n, tilecnt);

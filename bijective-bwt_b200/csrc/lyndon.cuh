@@ -7,8 +7,8 @@
 //                       T[b..n) until the pending factor starts at or after e.  That marks
 //                       exactly the positions of the chunk that are smaller than every
 //                       earlier suffix *starting in the same chunk* (a decreasing list).
-//   2. k_chunkmin_*     exclusive prefix minimum, in suffix order, of the chunks' last
-//                       marks (= each chunk's smallest suffix).
+//   2. k_chunkmin_*     prefix minimum, in suffix order, of the chunks' last marks (= each
+//                       chunk's smallest suffix): per-group reduce, Hillis-Steele levels.
 //   3. k_chunk_threshold a mark survives iff its suffix is below that minimum; survivors
 //                       are a tail of the chunk's list (binary search, warp-wide compares).
 #pragma once
@@ -22,13 +22,23 @@ static __device__ __forceinline__ bool suffix_less_warp(const u8 *__restrict__ T
     const u32 lane = lane_id();
     u32 off = 0;
     for (;;) {
-        const u32 pa = a + off + lane * 8, pb = b + off + lane * 8;
-        bool diff = true;  // lanes too close to the end defer to the byte loop
-        if ((u64)pa + 16 <= n && (u64)pb + 16 <= n) diff = load8_unaligned(T + pa) != load8_unaligned(T + pb);
-        const u32 mask = __ballot_sync(FULL_MASK, diff);
-        if (mask == 0) { off += 256; continue; }
+        // every lane checks 32 bytes (4 independent 8-byte compares), the warp 1 KiB per step
+        const u32 pa = a + off + lane * 32, pb = b + off + lane * 32;
+        u32 first = 4;  // index of my first differing (or unsafe) 8-byte word
+        if ((u64)pa + 40 <= n && (u64)pb + 40 <= n) {
+            u64 x[4], y[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { x[q] = load8_unaligned(T + pa + 8 * q); y[q] = load8_unaligned(T + pb + 8 * q); }
+#pragma unroll
+            for (int q = 3; q >= 0; q--) if (x[q] != y[q]) first = q;
+        } else {
+            first = 0;  // too close to the end: let the byte loop decide
+        }
+        const u32 mask = __ballot_sync(FULL_MASK, first < 4);
+        if (mask == 0) { off += 1024; continue; }
         const u32 l = __ffs(mask) - 1;
-        u32 p = a + off + l * 8, q = b + off + l * 8;
+        const u32 w = __shfl_sync(FULL_MASK, first, l);
+        u32 p = a + off + l * 32 + w * 8, q = b + off + l * 32 + w * 8;
         while (p < n && q < n) {
             const u8 ca = T[p], cb = T[q];
             if (ca != cb) return ca < cb;
@@ -49,13 +59,22 @@ __global__ void __launch_bounds__(128) k_duval_chunks(const u8 *__restrict__ T, 
     u32 f = b, last = b;
     while (f < e) {
         u32 i = f, k = f + 1;
+        bool settled = false;
         while (k < n) {
+            // past the chunk end only a repetition with a period short enough to put another
+            // copy inside the chunk is still undecided; anything else cannot mark more starts
+            if (k >= e && f + (k - i) >= e) { settled = true; break; }
             const u8 ci = T[i], ck = T[k];
             if (ci > ck) break;
             if (ci < ck) { i = f; k++; continue; }
             i++; k++;
             // inside a periodic stretch: skip 8 bytes at a time (i < k)
             while ((u64)k + 16 <= n && load8_unaligned(T + i) == load8_unaligned(T + k)) { i += 8; k += 8; }
+        }
+        if (settled) {  // T[f..] is one pending word reaching beyond the chunk: f is its only start
+            flags[f] = 1;
+            last = f;
+            break;
         }
         const u32 p = k - i;
         while (f <= i && f < e) {
@@ -89,34 +108,16 @@ __global__ void __launch_bounds__(128) k_chunkmin_reduce(const u8 *__restrict__ 
     if (lane_id() == 0) group_min[g] = run;
 }
 
-// single block of 32 warps: exclusive scan of group_min -> group_excl
-__global__ void __launch_bounds__(1024) k_chunkmin_scan(const u8 *__restrict__ T, u32 n,
-                                                        const u32 *__restrict__ group_min, u32 ngroups,
-                                                        u32 *__restrict__ group_excl)
+// one Hillis-Steele level of the inclusive prefix minimum over the groups (warp per group):
+// out[g] = min(in[g], in[g - stride]).  ceil(log2(ngroups)) launches, ping-pong buffers.
+__global__ void __launch_bounds__(128) k_chunkmin_level(const u8 *__restrict__ T, u32 n, const u32 *__restrict__ in,
+                                                        u32 *__restrict__ out, u32 ngroups, u32 stride)
 {
-    __shared__ u32 part[32];
-    const u32 warp = threadIdx.x >> 5, lane = lane_id();
-    const u32 per = (ngroups + 31) / 32;
-    const u32 lo = min(ngroups, warp * per), hi = min(ngroups, lo + per);
-    u32 run = NONE32;
-    for (u32 g = lo; g < hi; g++) run = suffix_min_warp(T, n, run, group_min[g]);
-    if (lane == 0) part[warp] = run;
-    __syncthreads();
-    if (warp == 0) {
-        u32 acc = NONE32;
-        for (u32 w = 0; w < 32; w++) {
-            const u32 mine = part[w];
-            __syncwarp();
-            if (lane == 0) part[w] = acc;
-            acc = suffix_min_warp(T, n, acc, mine);
-        }
-    }
-    __syncthreads();
-    run = part[warp];
-    for (u32 g = lo; g < hi; g++) {
-        if (lane == 0) group_excl[g] = run;
-        run = suffix_min_warp(T, n, run, group_min[g]);
-    }
+    const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= ngroups) return;
+    u32 v = in[g];
+    if (g >= stride) v = suffix_min_warp(T, n, in[g - stride], v);
+    if (lane_id() == 0) out[g] = v;
 }
 
 // ---- 3. per chunk: drop the marks that are not below the minimum of everything before ----
@@ -146,12 +147,12 @@ static __device__ void clear_flags_warp(u8 *flags, u32 lo, u32 hi)
 
 __global__ void __launch_bounds__(128) k_chunk_threshold(const u8 *__restrict__ T, u32 n, u32 chunk, u32 nch,
                                                          u8 *__restrict__ flags, const u32 *__restrict__ chunk_last,
-                                                         const u32 *__restrict__ group_excl, u32 ngroups)
+                                                         const u32 *__restrict__ group_incl, u32 ngroups)
 {
     const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= ngroups) return;
     const u32 lo = g * LY_GROUP, hi = min(nch, lo + LY_GROUP);
-    u32 run = group_excl[g];
+    u32 run = g ? group_incl[g - 1] : NONE32;
     for (u32 t = lo; t < hi; t++) {
         const u32 mlast = chunk_last[t];
         if (run != NONE32) {

@@ -37,9 +37,21 @@ def lyndon_starts_chunked(T, B):
         f = b
         while f < e:
             i, k = f, f + 1
-            while k < n and T[i] <= T[k]:
+            settled = False
+            while k < n:
+                # past the chunk end only a repetition whose period still puts another copy
+                # inside the chunk is undecided; otherwise nothing more can be marked
+                if k >= e and f + (k - i) >= e:
+                    settled = True
+                    break
+                if T[i] > T[k]:
+                    break
                 i = f if T[i] < T[k] else i + 1
                 k += 1
+            if settled:
+                flags[f] = 1
+                last[t] = f
+                break
             p = k - i
             while f <= i and f < e:
                 flags[f] = 1

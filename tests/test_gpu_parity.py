@@ -207,3 +207,16 @@ def test_cli_tools_match_reference_layout(oracle, gen, tmp_path):
     env = dict(os.environ, BWTS_B200_BLOCK="131072")
     out = subprocess.run([str(bindir / "mk_bwts"), str(src)], capture_output=True, check=True, env=env).stdout
     assert out == b"".join(oracle.forward(x[o:o + 131072]) for o in range(0, len(x), 131072))
+
+
+def test_context_reuse_across_sizes(ctx, oracle, gen):
+    """one context, large and small inputs interleaved: the workspace is re-laid-out per call
+    and must not depend on what an earlier transform left behind (regression: stale keys in
+    the look-back status region were read as live status words)"""
+    seq = [("text", 2, 300_000), ("dna", 4, 100_000), ("random", 3, 700_001), ("dna", 4, 100_000),
+           ("text", 8, 50_000), ("tiled", 3, 1_200_000), ("dna", 9, 33_333), ("text", 2, 300_000)]
+    for kind, seed, n in seq:
+        x = gen.make(kind, seed, n)
+        y = ctx.forward_host(x)
+        assert y == oracle.forward(x), (kind, seed, n)
+        assert ctx.inverse_host(y) == x, (kind, seed, n)
