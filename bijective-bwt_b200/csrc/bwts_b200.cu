@@ -53,7 +53,7 @@ struct bwts_b200_ctx {
     std::vector<LaunchRec> recs;
     std::vector<cudaEvent_t> pool;
     size_t pool_used = 0;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_io0 = nullptr, ev_io1 = nullptr;
     bwts_b200_stats stats;
     u32 epoch = 0;
 };
@@ -460,7 +460,8 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc((void **)&ctx->h_small, 4096, cudaHostAllocDefault) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev_begin) != cudaSuccess || cudaEventCreate(&ctx->ev_end) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev_begin) != cudaSuccess || cudaEventCreate(&ctx->ev_end) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_io0) != cudaSuccess || cudaEventCreate(&ctx->ev_io1) != cudaSuccess) {
         bwts_b200_destroy(ctx);
         return nullptr;
     }
@@ -475,6 +476,8 @@ extern "C" void bwts_b200_destroy(bwts_b200_ctx *ctx)
     for (cudaEvent_t e : ctx->pool) cudaEventDestroy(e);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->ev_io0) cudaEventDestroy(ctx->ev_io0);
+    if (ctx->ev_io1) cudaEventDestroy(ctx->ev_io1);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->io_in) cudaFree(ctx->io_in);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -535,6 +538,7 @@ static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, 
     ctx->io_in = nullptr;
     u8 *d_in = ctx->arena, *d_out = ctx->arena + ctx->io_bytes;
     cudaStream_t st = ctx->own_stream;
+    CK(cudaEventRecord(ctx->ev_io0, st));
     CK(cudaMemcpyAsync(d_in, in, (size_t)len, cudaMemcpyHostToDevice, st));
     ctx->io_in = d_in;  // tells the cores to skip the I/O region of the arena
     stats_begin(ctx, len, direction, st);
@@ -544,7 +548,11 @@ static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, 
     if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
     stats_end(ctx, st);
     CK(cudaMemcpyAsync(out, d_out, (size_t)len, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev_io1, st));
     CK(cudaStreamSynchronize(st));
+    float t = 0;
+    if (cudaEventElapsedTime(&t, ctx->ev_io0, ctx->ev_begin) == cudaSuccess) ctx->stats.h2d_ms = t;
+    if (cudaEventElapsedTime(&t, ctx->ev_end, ctx->ev_io1) == cudaSuccess) ctx->stats.d2h_ms = t;
     return 0;
 }
 

@@ -106,6 +106,9 @@ typedef struct {
     long   class_launches[BWTS_B200_NCLASS];
     double class_ms[BWTS_B200_NCLASS];
     double class_bytes[BWTS_B200_NCLASS];
+    /* host-buffer entry points only: CUDA-event times of the two copies around the transform */
+    double h2d_ms;
+    double d2h_ms;
 } bwts_b200_stats;
 
 int bwts_b200_get_stats(const bwts_b200_ctx *ctx, bwts_b200_stats *out);
