@@ -209,6 +209,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         n = args.bytes
     data = make_input(kind_name, seed + 100 * rank, n)
 
+    for kv in args.tune:
+        k, v = kv.split(":")
+        bwts.tune(int(k), int(v))
     ctx = bwts.Context(local_rank)
     ctx.reserve(n)
     host_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
@@ -377,6 +380,7 @@ def main():
     ap.add_argument("--bytes", type=int, default=0, help="override the block size (diagnostics only)")
     ap.add_argument("--cpu-sample", type=int, default=64 << 20, help="bytes of the block the CPU baseline runs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tune", action="append", default=[], help="key:value for bwts_b200_tune (experiments)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -37,6 +37,7 @@ static const char *kclass_names[BWTS_B200_NCLASS] = {
 static std::atomic<u32> g_epoch{0};  // onesweep status epoch, unique per pass across all contexts
 static long g_tune_chunk = 0;      // Lyndon chunk bytes (0 = auto)
 static long g_tune_spl_shift = 0;  // splitter shift   (0 = 26)
+static long g_tune_onesweep = 0;   // onesweep tile configuration (see radix_sort)
 
 struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; };
 
@@ -171,14 +172,31 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
     const u32 hgrid = min(cdiv(m, 256), 148u * 8u);
     LAUNCH(KC_RADIX_HIST, 8.0 * m, k_radix_hist, hgrid, 256, sb.k[sb.cur], m, passes, sb.hist);
     LAUNCH(KC_RADIX_HIST, 0, k_radix_hist_scan, passes, 256, sb.hist);
-    const u32 tiles = cdiv(m, OS_TILE);
     for (int p = 0; p < passes; p++) {
         const int a = sb.cur, b = sb.cur ^ 1;
         const bool ident = identity_vals && p == 0;
         do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
-        LAUNCH(KC_ONESWEEP, (ident ? 20.0 : 24.0) * m, k_onesweep_pass, tiles, OS_NT, sb.k[a],
-               ident ? (const u32 *)nullptr : sb.v[a], sb.k[b], sb.v[b], m, (u32)(p * RADIX_BITS),
-               sb.hist + p * RADIX_BINS, sb.status, tickets + p, ctx->epoch);
+        const u32 *vin = ident ? (const u32 *)nullptr : sb.v[a];
+        const double bytes = (ident ? 20.0 : 24.0) * m;
+#define OS_LAUNCH(NT_, IPT_, MINB_, LB_)                                                                  \
+    do {                                                                                                  \
+        LaunchRec r__;                                                                                    \
+        r__.cls = KC_ONESWEEP; r__.bytes = bytes; r__.e0 = r__.e1 = nullptr;                              \
+        if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }           \
+        k_onesweep_pass<NT_, IPT_, MINB_, LB_><<<cdiv(m, (NT_) * (IPT_)), NT_, OsSmem<NT_, IPT_>::bytes, st>>>( \
+            sb.k[a], vin, sb.k[b], sb.v[b], m, (u32)(p * RADIX_BITS), sb.hist + p * RADIX_BINS, sb.status,  \
+            tickets + p, ctx->epoch);                                                                     \
+        if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
+        ctx->recs.push_back(r__);                                                                         \
+        CK(cudaGetLastError());                                                                           \
+    } while (0)
+        switch (g_tune_onesweep) {
+        case 1: OS_LAUNCH(512, 8, 2, 8); break;
+        case 2: OS_LAUNCH(512, 8, 2, 32); break;
+        case 3: OS_LAUNCH(256, 8, 4, 16); break;
+        default: OS_LAUNCH(512, 8, 2, 16); break;
+        }
+#undef OS_LAUNCH
         sb.cur = b;
         ctx->stats.radix_passes++;
     }
@@ -196,7 +214,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
 
     const u32 ntl = cdiv(n, FL_TILE);
     const u32 nblk = cdiv(n, 1u << COARSE_BITS);
-    const u32 os_tiles = cdiv(n, OS_TILE), rr_tiles = cdiv(n, RR_TILE);
+    const u32 os_tiles = cdiv(n, OS_TILE_MIN), rr_tiles = cdiv(n, RR_TILE);
 
     SortBufs sb;
     sb.k[0] = arena_take<u64>(ctx, n);
@@ -230,7 +248,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
 
     if (!linear) {
         // -- Lyndon boundaries
-        u32 chunk = g_tune_chunk > 0 ? (u32)g_tune_chunk : max(2048u, cdiv(n, 65536));
+        u32 chunk = g_tune_chunk > 0 ? (u32)g_tune_chunk : max(512u, cdiv(n, 1u << 21));
         const u32 nch = cdiv(n, chunk), ngroups = cdiv(nch, LY_GROUP);
         u32 *chunk_last = arena_take<u32>(ctx, nch);
         u32 *group_min = arena_take<u32>(ctx, ngroups);
@@ -455,6 +473,16 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
 {
     if (device < 0 || device >= bwts_b200_device_count()) return nullptr;
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    // the sort kernels use > 48 KB of dynamic shared memory and want the large carveout
+#define OS_ATTR(NT_, IPT_, MINB_, LB_)                                                                          \
+    cudaFuncSetAttribute(k_onesweep_pass<NT_, IPT_, MINB_, LB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                         (int)OsSmem<NT_, IPT_>::bytes);                                                         \
+    cudaFuncSetAttribute(k_onesweep_pass<NT_, IPT_, MINB_, LB_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+    OS_ATTR(512, 8, 2, 8);
+    OS_ATTR(512, 8, 2, 32);
+    OS_ATTR(256, 8, 4, 16);
+    OS_ATTR(512, 8, 2, 16);
+#undef OS_ATTR
     bwts_b200_ctx *ctx = new bwts_b200_ctx();
     ctx->device = device;
     memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -712,5 +740,6 @@ extern "C" int bwts_b200_tune(int key, long value)
 {
     if (key == 0) { if (value < 0) return BWTS_B200_EINVAL; g_tune_chunk = value; return 0; }
     if (key == 1) { if (value != 0 && (value < 20 || value > 31)) return BWTS_B200_EINVAL; g_tune_spl_shift = value; return 0; }
+    if (key == 2) { if (value < 0 || value > 3) return BWTS_B200_EINVAL; g_tune_onesweep = value; return 0; }
     return BWTS_B200_EINVAL;
 }

@@ -15,10 +15,9 @@
 #define RADIX_BINS 256
 #define RADIX_MAX_PASSES 8
 
-#define OS_NT 256                 // threads per CTA
-#define OS_IPT 16                 // keys per thread
-#define OS_TILE (OS_NT * OS_IPT)  // 4096 keys per tile
-#define OS_NW (OS_NT / 32)
+#define OS_TILE_MAX 4096          // status array is sized for the smallest tile in use (2048)
+#define OS_TILE_MIN 2048
+#define OS_LOOKBACK 8             // status words fetched per look-back step
 
 #define OS_FLAG_AGG 1ull
 #define OS_FLAG_PREFIX 2ull
@@ -76,50 +75,79 @@ __global__ void __launch_bounds__(256) k_radix_hist_scan(u32 *__restrict__ ghist
 
 // ---- one onesweep pass -----------------------------------------------------------------
 // vin == nullptr means "values are the element indices" (first pass of the initial sort).
-__global__ void __launch_bounds__(OS_NT) k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin,
-                                                         u64 *__restrict__ kout, u32 *__restrict__ vout, u32 m,
-                                                         u32 shift, const u32 *__restrict__ binbase,
-                                                         u64 *__restrict__ status, u32 *__restrict__ ticket,
-                                                         u32 epoch)
+// NT threads x IPT keys per thread = one tile; MINB = CTAs per SM the register budget allows;
+// LB = status words fetched per look-back step.  The look-back is the serial part of the
+// kernel (tiles/s <= LB / L2 latency), so it runs after keys and values have left the
+// registers for shared memory -- that staging needs only tile-local offsets.
+template <int NT, int IPT>
+struct OsSmem {
+    static constexpr int TILE = NT * IPT, NW = NT / 32;
+    static constexpr size_t keys = 0;                                   // u64[TILE]
+    static constexpr size_t vals = keys + sizeof(u64) * TILE;           // u32[TILE]
+    static constexpr size_t wcnt = vals + sizeof(u32) * TILE;           // u16[NW][256]
+    static constexpr size_t dstart = wcnt + sizeof(u16) * NW * RADIX_BINS;  // u32[256]
+    static constexpr size_t adj = dstart + sizeof(u32) * RADIX_BINS;    // u32[256]
+    static constexpr size_t wsum = adj + sizeof(u32) * RADIX_BINS;      // u32[8]
+    static constexpr size_t tile = wsum + sizeof(u32) * 8;              // u32
+    static constexpr size_t dig = tile + 16;                            // u8[TILE]
+    static constexpr size_t bytes = dig + TILE;
+};
+
+template <int NT, int IPT, int MINB, int LB>
+__global__ void __launch_bounds__(NT, MINB)
+k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout,
+                u32 *__restrict__ vout, u32 m, u32 shift, const u32 *__restrict__ binbase,
+                u64 *__restrict__ status, u32 *__restrict__ ticket, u32 epoch)
 {
-    __shared__ __align__(16) u64 s_keys[OS_TILE];  // reused for the values
-    __shared__ u32 s_wcnt[OS_NW][RADIX_BINS];
-    __shared__ u32 s_dstart[RADIX_BINS];
-    __shared__ u32 s_adj[RADIX_BINS];
-    __shared__ u8 s_dig[OS_TILE];
-    __shared__ u32 s_wsum[OS_NW];
-    __shared__ u32 s_tile;
+    using L = OsSmem<NT, IPT>;
+    constexpr int TILE = L::TILE, NW = L::NW;
+    static_assert(NT >= RADIX_BINS && TILE <= 65536, "one thread per digit; 16-bit tile positions");
+    extern __shared__ __align__(16) u8 smem[];
+    u64 *s_keys = (u64 *)(smem + L::keys);
+    u32 *s_vals = (u32 *)(smem + L::vals);
+    u16(*s_wcnt)[RADIX_BINS] = (u16(*)[RADIX_BINS])(smem + L::wcnt);
+    u32 *s_dstart = (u32 *)(smem + L::dstart);
+    u32 *s_adj = (u32 *)(smem + L::adj);
+    u32 *s_wsum = (u32 *)(smem + L::wsum);
+    u32 *s_tile = (u32 *)(smem + L::tile);
+    u8 *s_dig = smem + L::dig;
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (u32 i = tid; i < OS_NW * RADIX_BINS; i += OS_NT) ((u32 *)s_wcnt)[i] = 0;
+    if (tid == 0) *s_tile = atomicAdd(ticket, 1u);
+    for (u32 i = tid; i < NW * RADIX_BINS / 2; i += NT) ((u32 *)s_wcnt)[i] = 0;
     __syncthreads();
-    const u32 tile = s_tile;
-    const u32 base = tile * OS_TILE;
-    const u32 cnt = min((u32)OS_TILE, m - base);
-    const u32 wbase = base + warp * (32 * OS_IPT);
+    const u32 tile = *s_tile;
+    const u32 base = tile * TILE;
+    const u32 cnt = min((u32)TILE, m - base);
+    const u32 wbase = base + warp * (32 * IPT);
 
-    // warp-striped load: slot j of lane l is tile position warp*512 + j*32 + l
-    u64 key[OS_IPT];
+    // warp-striped loads: slot j of lane l is tile position warp*32*IPT + j*32 + l
+    u64 key[IPT];
+    u32 val[IPT];
 #pragma unroll
-    for (int j = 0; j < OS_IPT; j++) {
+    for (int j = 0; j < IPT; j++) {
         const u32 g = wbase + j * 32 + lane;
         key[j] = (g < m) ? ldg_stream_u64(kin + g) : ~0ull;  // pads: digit 255, last in tile order
     }
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        const u32 g = wbase + j * 32 + lane;
+        val[j] = (g < m) ? (vin ? ldg_stream_u32(vin + g) : g) : 0u;
+    }
 
     // rank inside the warp, in slot order (stable)
-    u32 *wc = s_wcnt[warp];
+    u16 *wc = s_wcnt[warp];
     const u32 lt = lanemask_lt();
-    u16 rnk[OS_IPT];
+    u16 rnk[IPT];
 #pragma unroll
-    for (int j = 0; j < OS_IPT; j++) {
+    for (int j = 0; j < IPT; j++) {
         const u32 d = (u32)(key[j] >> shift) & (RADIX_BINS - 1);
         const u32 peers = __match_any_sync(FULL_MASK, d);
         const int leader = __ffs(peers) - 1;
         u32 before = 0;
         if ((int)lane == leader) {
             before = wc[d];
-            wc[d] = before + __popc(peers);
+            wc[d] = (u16)(before + __popc(peers));
         }
         before = __shfl_sync(FULL_MASK, before, leader);
         rnk[j] = (u16)(before + __popc(peers & lt));
@@ -127,69 +155,80 @@ __global__ void __launch_bounds__(OS_NT) k_onesweep_pass(const u64 *__restrict__
     }
     __syncthreads();
 
-    // per digit (thread d): exclusive offsets of the warps, tile count
+    // one thread per digit: exclusive offsets of the warps, tile count, publish the aggregate
+    u32 blockcnt = 0, dsum = 0;
     const u32 d = tid;
-    u32 blockcnt = 0;
-#pragma unroll
-    for (int w = 0; w < OS_NW; w++) {
-        const u32 c = s_wcnt[w][d];
-        s_wcnt[w][d] = blockcnt;
-        blockcnt += c;
-    }
-
-    // publish, then look back over earlier tiles
     u64 *my = status + (u64)tile * RADIX_BINS + d;
-    u32 excl = 0;
-    if (tile == 0) {
-        st_relaxed_u64(my, os_pack(epoch, OS_FLAG_PREFIX, blockcnt));
-    } else {
-        st_relaxed_u64(my, os_pack(epoch, OS_FLAG_AGG, blockcnt));
-        const u64 *p = my - RADIX_BINS;
-        for (;;) {
-            const u64 v = ld_relaxed_u64(p);
-            if ((u32)(v >> 34) != epoch) continue;  // not written in this pass yet
-            excl += (u32)v;
-            if (((v >> 32) & 3ull) == OS_FLAG_PREFIX) break;
-            p -= RADIX_BINS;
+    if (tid < RADIX_BINS) {
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const u32 c = s_wcnt[w][d];
+            s_wcnt[w][d] = (u16)blockcnt;
+            blockcnt += c;
         }
-        st_relaxed_u64(my, os_pack(epoch, OS_FLAG_PREFIX, excl + blockcnt));
+        st_relaxed_u64(my, os_pack(epoch, tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG, blockcnt));
+        const u32 incl = warp_incl_sum(blockcnt);
+        if (lane == 31) s_wsum[warp] = incl;
+        dsum = incl - blockcnt;  // exclusive sum inside my warp of digits
     }
-
-    // where each digit's run starts inside the sorted tile
-    const u32 incl = warp_incl_sum(blockcnt);
-    if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
-    u32 woff = 0;
+    if (tid < RADIX_BINS) {
 #pragma unroll
-    for (int w = 0; w < OS_NW; w++)
-        if (w < (int)warp) woff += s_wsum[w];
-    const u32 dstart = woff + incl - blockcnt;
-    s_dstart[d] = dstart;
-    s_adj[d] = __ldg(binbase + d) + excl - dstart;
+        for (int w = 0; w < RADIX_BINS / 32; w++)
+            if (w < (int)warp) dsum += s_wsum[w];
+        s_dstart[d] = dsum;  // where the digit's run starts inside the sorted tile
+    }
     __syncthreads();
 
-    // keys -> shared memory in tile-sorted order
+    // keys and values -> shared memory in tile-sorted order (frees their registers)
 #pragma unroll
-    for (int j = 0; j < OS_IPT; j++) {
+    for (int j = 0; j < IPT; j++) {
         const u32 dj = (u32)(key[j] >> shift) & (RADIX_BINS - 1);
         const u32 pos = s_dstart[dj] + wc[dj] + rnk[j];
         s_keys[pos] = key[j];
+        s_vals[pos] = val[j];
         s_dig[pos] = (u8)dj;
-        rnk[j] = (u16)pos;
     }
-    __syncthreads();
-#pragma unroll 4
-    for (u32 s = tid; s < cnt; s += OS_NT) kout[s + s_adj[s_dig[s]]] = s_keys[s];
+
+    // decoupled look-back over the earlier tiles, LB status words per step
+    if (tid < RADIX_BINS) {
+        u32 excl = 0;
+        if (tile != 0) {
+            int t = (int)tile - 1;
+            bool found = false;
+            while (!found) {
+                u64 v[LB];
+#pragma unroll
+                for (int q = 0; q < LB; q++) {
+                    const int tt = t - q;
+                    v[q] = (tt >= 0) ? ld_relaxed_u64(status + (u64)tt * RADIX_BINS + d)
+                                     : os_pack(epoch, OS_FLAG_PREFIX, 0);
+                }
+                int used = 0;
+#pragma unroll
+                for (int q = 0; q < LB; q++) {
+                    if (found || used != q) continue;          // stopped earlier in this window
+                    if ((u32)(v[q] >> 34) != epoch) continue;  // not published yet: re-read from here
+                    excl += (u32)v[q];
+                    used = q + 1;
+                    if (((v[q] >> 32) & 3ull) == OS_FLAG_PREFIX) found = true;
+                }
+                t -= used;
+            }
+            st_relaxed_u64(my, os_pack(epoch, OS_FLAG_PREFIX, excl + blockcnt));
+        }
+        s_adj[d] = __ldg(binbase + d) + excl - dsum;
+    }
     __syncthreads();
 
-    // values take the same route
-    u32 *s_vals = (u32 *)s_keys;
+    // every digit run goes out with consecutive threads on consecutive addresses
 #pragma unroll
-    for (int j = 0; j < OS_IPT; j++) {
-        const u32 g = wbase + j * 32 + lane;
-        if (g < m) s_vals[rnk[j]] = vin ? ldg_stream_u32(vin + g) : g;
+    for (int q = 0; q < IPT; q++) {
+        const u32 s = q * NT + tid;
+        if (s < cnt) {
+            const u32 dst = s + s_adj[s_dig[s]];
+            kout[dst] = s_keys[s];
+            vout[dst] = s_vals[s];
+        }
     }
-    __syncthreads();
-#pragma unroll 4
-    for (u32 s = tid; s < cnt; s += OS_NT) vout[s + s_adj[s_dig[s]]] = s_vals[s];
 }

@@ -121,7 +121,7 @@ const char *bwts_b200_version(void);
 
 /* Test hooks: override tuning constants so that small inputs exercise the multi-tile /
  * multi-chunk paths.  key: 0 = Lyndon chunk bytes (>= 1), 1 = inverse splitter shift
- * (density 2^-(32-shift), 20..31), 2 = reserved.  value 0 restores the default.       */
+ * (density 2^-(32-shift), 20..31), 2 = onesweep tile shape (0..3).  value 0 = default.       */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */
