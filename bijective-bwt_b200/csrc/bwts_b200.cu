@@ -28,16 +28,17 @@
 
 enum KClass {
     KC_LYNDON = 0, KC_FACTORS, KC_INIT_KEYS, KC_RADIX_HIST, KC_ONESWEEP, KC_BUILD_KEYS, KC_RERANK, KC_EMIT,
-    KC_INV_HIST, KC_INV_LF, KC_INV_WALK, KC_INV_JUMP, KC_INV_SCAN, KC_INV_PLACE, KC_MISC, KC_COPY
+    KC_INV_HIST, KC_INV_LF, KC_INV_WALK, KC_INV_JUMP, KC_INV_SCAN, KC_INV_PLACE, KC_LOCAL_SORT, KC_COPY
 };
 static const char *kclass_names[BWTS_B200_NCLASS] = {
     "lyndon", "factor_table", "init_keys", "radix_hist", "onesweep_pass", "build_keys", "rerank", "emit",
-    "inv_tile_hist", "inv_lf_rank", "inv_walk", "inv_jump", "inv_scan", "inv_place", "misc", "copy"};
+    "inv_tile_hist", "inv_lf_rank", "inv_walk", "inv_jump", "inv_scan", "inv_place", "local_sort", "copy"};
 
 static std::atomic<u32> g_epoch{0};  // onesweep status epoch, unique per pass across all contexts
 static long g_tune_chunk = 0;      // Lyndon chunk bytes (0 = auto)
 static long g_tune_spl_shift = 0;  // splitter shift   (0 = 26)
 static long g_tune_onesweep = 0;   // onesweep tile configuration (see radix_sort)
+static long g_tune_local = 0;      // 1 = never use the warp-local sort path
 
 struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; };
 
@@ -139,9 +140,9 @@ static T *arena_take(bwts_b200_ctx *ctx, size_t count)
 }
 static size_t workspace_bytes(size_t n)
 {
-    // forward is the larger of the two: keys 2x8, idx/grp/gst 2x4 each, rank 4, FS 4,
-    // flags 1, onesweep status n/2, misc
-    return n * 72 + (64u << 20);
+    // forward is the larger of the two: L set keys 2x8 + idx/grp/gst 2x4 each, S set keys 8 +
+    // idx/grp/gst 2x4 each, rank 4, FS 4, flags 1, onesweep status n, misc
+    return n * 106 + (64u << 20);
 }
 
 static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
@@ -231,11 +232,17 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     u32 *cidx = arena_take<u32>(ctx, (size_t)nblk + 2);
     u8 *flags = arena_take<u8>(ctx, n);
     u32 *tilecnt = arena_take<u32>(ctx, ntl + 1);
-    u64 *rr_status = arena_take<u64>(ctx, rr_tiles + 1);
+    u64 *rr_statusA = arena_take<u64>(ctx, rr_tiles + 1);
+    u64 *rr_statusB = arena_take<u64>(ctx, rr_tiles + 1);
+    u64 *kS = arena_take<u64>(ctx, n);
+    u32 *vS[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
+    u32 *grpS[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
+    u32 *gstS[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
     u32 *small = arena_take<u32>(ctx, 1024);  // [0] F, [1] lmax, [2] sigma, [8..15] presence, [16..] rerank counters
     u8 *code = (u8 *)arena_take<u32>(ctx, 64);
     if (!sb.k[0] || !sb.k[1] || !sb.v[0] || !sb.v[1] || !sb.hist || !sb.status || !grp[0] || !grp[1] || !gst[0] ||
-        !gst[1] || !rank || !FS || !cidx || !flags || !tilecnt || !rr_status || !small || !code)
+        !gst[1] || !rank || !FS || !cidx || !flags || !tilecnt || !rr_statusA || !rr_statusB || !small || !code || !kS ||
+        !vS[0] || !vS[1] || !grpS[0] || !grpS[1] || !gstS[0] || !gstS[1])
         return BWTS_B200_EINTERNAL;
     RerankCounters *rrc = (RerankCounters *)(small + 16);
 
@@ -306,57 +313,112 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     CK(cudaMemsetAsync(grp[0], 0, (size_t)n * 4, st));
     CK(cudaMemsetAsync(gst[0], 0, (size_t)n * 4, st));
 
-    int g = 0;  // current grp/gst buffers
-    u32 m = n, groups_before = 1;
+    // Two live sets.  L: groups of any size, sorted by the global radix path (sb, grp, gst).
+    // S: groups of at most 32 members, sorted warp-locally (kS, vS, grpS, gstS).
+    int g = 0, gs = 0, cs = 0;       // current buffers of grp/gst (L), grpS/gstS, vS
+    u32 mL = n, mS = 0, groups_before = 1;
     u64 k = k0;
     const u32 kb = linear ? bit_length(n) : max(1, bit_length((u64)n - 1));
-    bool first = true;
+    bool first = true, sortedL = true;  // the L set enters the loop freshly sorted (initial sort)
+    bool sortedS = false;
     for (;;) {
-        // re-rank the freshly sorted live array, compact
-        CK(cudaMemsetAsync(rr_status, 0, (size_t)cdiv(m, RR_TILE) * 8, st));
-        CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
-        LAUNCH(KC_RERANK, 24.0 * m, k_rerank, cdiv(m, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur], grp[g], gst[g], m,
-               0, rank, sb.v[sb.cur ^ 1], grp[g ^ 1], gst[g ^ 1], rr_status, rrc);
-        rc = readback(ctx, st, rrc, sizeof(RerankCounters));
+        // ---- re-rank what was just sorted; S first, L appends to the same S stream
+        CK(cudaMemsetAsync(rrc, 0, 2 * sizeof(RerankCounters), st));
+        LiveOut oS = {vS[cs], grpS[gs ^ 1], gstS[gs ^ 1]};
+        if (mS && sortedS) {
+            CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
+            CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
+            LiveOut none = {nullptr, nullptr, nullptr};
+            LAUNCH(KC_RERANK, 24.0 * mS, k_rerank<false>, cdiv(mS, RR_TILE), RR_NT, kS, vS[cs ^ 1], grpS[gs],
+                   gstS[gs], mS, 0, rank, oS, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0);
+        }
+        if (mL && sortedL) {
+            CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
+            CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
+            LiveOut oL = {sb.v[sb.cur ^ 1], grp[g ^ 1], gst[g ^ 1]};
+            if (g_tune_local) {
+                LiveOut none = {nullptr, nullptr, nullptr};
+                LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<false>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
+                       grp[g], gst[g], mL, 0, rank, oL, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 1);
+            } else {
+                LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<true>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
+                       grp[g], gst[g], mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL, rr_statusA, rr_statusB,
+                       rrc + 1);
+            }
+        }
+        rc = readback(ctx, st, rrc, 2 * sizeof(RerankCounters));
         if (rc) return rc;
-        const RerankCounters c = *(const RerankCounters *)ctx->h_small;
-        ctx->stats.class_bytes[KC_RERANK] += 12.0 * c.kept;
+        const RerankCounters cS = ((const RerankCounters *)ctx->h_small)[0];
+        const RerankCounters cL = ((const RerankCounters *)ctx->h_small)[1];
         if (first && !linear) {
             rc = readback(ctx, st, small + 1, 4);
             if (rc) return rc;
             lmax = ctx->h_small[0];
-            first = false;
         }
-        const bool split = c.heads != groups_before;
+        first = false;
+        u32 newS, newL;
+        if (g_tune_local) {  // routing off: the "S" stream of the L re-rank is the L set itself
+            newS = 0;
+            newL = cL.keptS;
+        } else {
+            newS = cS.keptS + cL.keptS;
+            newL = cL.keptL;
+        }
+        ctx->stats.class_bytes[KC_RERANK] += 12.0 * ((double)newS + newL);
+        const bool split = cS.heads + cL.heads != groups_before;
         // adopt the compacted arrays
-        sb.cur ^= 1;  // idx now lives in v[cur]; k[cur] is scratch for the next key build
-        g ^= 1;
-        m = c.kept;
-        groups_before = c.kheads;
-        if (m == 0) break;
+        if (mL && sortedL) { sb.cur ^= 1; g ^= 1; }   // idx of L now lives in sb.v[cur]
+        if (!g_tune_local) gs ^= 1;                    // S stream was written to vS[cs], grpS/gstS[gs^1]
+        mS = newS;
+        mL = newL;
+        groups_before = cS.kheads + cL.kheads;
+        if (mS + mL == 0) break;
         const bool deep_enough = !linear && k >= 2ull * lmax;  // Fine-Wilf: remaining ties are equal rotations
         if (!split || deep_enough) {
             if (linear) return BWTS_B200_EINTERNAL;  // suffixes are pairwise distinct
             // ties are final: give every member of a tie its own slot
-            CK(cudaMemsetAsync(rr_status, 0, (size_t)cdiv(m, RR_TILE) * 8, st));
-            CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
-            LAUNCH(KC_RERANK, 16.0 * m, k_rerank, cdiv(m, RR_TILE), RR_NT, (const u64 *)nullptr, sb.v[sb.cur], grp[g],
-                   gst[g], m, 1, rank, (u32 *)nullptr, (u32 *)nullptr, (u32 *)nullptr, rr_status, rrc);
+            LiveOut none = {nullptr, nullptr, nullptr};
+            if (mS) {
+                CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
+                CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
+                CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
+                LAUNCH(KC_RERANK, 16.0 * mS, k_rerank<false>, cdiv(mS, RR_TILE), RR_NT, (const u64 *)nullptr, vS[cs],
+                       grpS[gs], gstS[gs], mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc);
+            }
+            if (mL) {
+                CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
+                CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
+                CK(cudaMemsetAsync(rrc + 1, 0, sizeof(RerankCounters), st));
+                LAUNCH(KC_RERANK, 16.0 * mL, k_rerank<false>, cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
+                       sb.v[sb.cur], grp[g], gst[g], mL, 1, rank, none, (const u32 *)nullptr, none, rr_statusA,
+                       rr_statusB, rrc + 1);
+            }
             break;
         }
-        // one doubling round on the live set
+        // ---- one doubling round on both live sets
         ctx->stats.rounds++;
-        ctx->stats.live_sum += m;
-        if (!linear) {
-            LAUNCH(KC_BUILD_KEYS, 20.0 * m, k_build_keys, cdiv(m, 256), 256, sb.v[sb.cur], gst[g], m, rank, FS, cidx,
-                   (u32)k, kb, sb.k[sb.cur]);
-        } else {
-            LAUNCH(KC_BUILD_KEYS, 20.0 * m, k_build_keys_linear, cdiv(m, 256), 256, sb.v[sb.cur], gst[g], m, rank, n,
-                   (u32)k, kb, sb.k[sb.cur]);
+        ctx->stats.live_sum += (long)mS + mL;
+        sortedS = sortedL = false;
+        if (mS) {
+            // every group fits a warp: gather + in-register ordering, no radix passes
+            LAUNCH(KC_LOCAL_SORT, 32.0 * mS, k_local_sort_warp, cdiv((u64)cdiv(mS, 32) * 32, 256), 256, vS[cs],
+                   gstS[gs], mS, rank, FS, cidx, (u32)k, kb, n, linear, kS, vS[cs ^ 1]);
+            ctx->stats.local_rounds++;
+            sortedS = true;
         }
-        const int passes = (int)cdiv((u64)kb + max(1, bit_length((u64)m - 1)), 8);
-        rc = radix_sort(ctx, st, sb, m, passes, false);
-        if (rc) return rc;
+        if (mL) {
+            if (!linear) {
+                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys, cdiv(mL, 256), 256, sb.v[sb.cur], gst[g], mL, rank, FS,
+                       cidx, (u32)k, kb, sb.k[sb.cur]);
+            } else {
+                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys_linear, cdiv(mL, 256), 256, sb.v[sb.cur], gst[g], mL,
+                       rank, n, (u32)k, kb, sb.k[sb.cur]);
+            }
+            const int passes = (int)cdiv((u64)kb + max(1, bit_length((u64)mL - 1)), 8);
+            rc = radix_sort(ctx, st, sb, mL, passes, false);
+            if (rc) return rc;
+            sortedL = true;
+        }
         k *= 2;
     }
 
@@ -740,6 +802,7 @@ extern "C" int bwts_b200_tune(int key, long value)
 {
     if (key == 0) { if (value < 0) return BWTS_B200_EINVAL; g_tune_chunk = value; return 0; }
     if (key == 1) { if (value != 0 && (value < 20 || value > 31)) return BWTS_B200_EINVAL; g_tune_spl_shift = value; return 0; }
+    if (key == 3) { g_tune_local = value; return 0; }
     if (key == 2) { if (value < 0 || value > 3) return BWTS_B200_EINVAL; g_tune_onesweep = value; return 0; }
     return BWTS_B200_EINVAL;
 }

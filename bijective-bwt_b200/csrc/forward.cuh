@@ -142,98 +142,211 @@ __global__ void __launch_bounds__(256) k_build_keys_linear(const u32 *__restrict
 }
 
 // ---- re-rank + compaction -----------------------------------------------------------------------
+// One pass over a freshly sorted live array: split groups where the sorted keys change, write
+// the new ranks, drop rotations that became unique and compact the rest into the next live
+// arrays.  Two output streams: S takes groups known to have at most 32 members (they are
+// re-sorted by k_local_sort_warp from then on), L the others (global radix path).  A group's
+// size is taken from the tile's own head flags; a group that touches a tile border counts
+// as large -- that only costs speed, never correctness.
 #define RR_NT 256
 #define RR_IPT 8
 #define RR_TILE (RR_NT * RR_IPT)
 #define RR_FLAG_AGG 1ull
 #define RR_FLAG_PREFIX 2ull
-// status word: flag[63:62] | (last head position + 1)[61:31] | kept count[30:0]
-static __device__ __forceinline__ u64 rr_pack(u64 flag, u32 headp1, u32 keep)
+#define RR_SMALL 32
+// status words: A = flag[63:62] | (last head position + 1)[61:31] | kept in S [30:0]
+//               B = flag[63:62] | kept in L [31:0]
+static __device__ __forceinline__ u64 rr_packA(u64 flag, u32 headp1, u32 keep)
 {
     return (flag << 62) | ((u64)headp1 << 31) | (u64)keep;
 }
+static __device__ __forceinline__ u64 rr_packB(u64 flag, u32 keep) { return (flag << 62) | (u64)keep; }
 
 struct RerankCounters {  // zeroed before each launch
     u32 ticket;
-    u32 heads;   // groups after the split (all of them)
-    u32 kheads;  // groups that stay live
-    u32 kept;    // live elements after compaction
+    u32 heads;    // groups after the split (all of them)
+    u32 kheads;   // groups that stay live (both streams)
+    u32 keptS;    // live elements compacted into the S stream
+    u32 keptL;    // live elements compacted into the L stream
+    u32 pad[3];
 };
 
-// finalize != 0: every element becomes its own group (used once ties are known to be final).
+struct LiveOut {  // one compaction stream
+    u32 *idx, *grp, *gst;
+};
+
+// ROUTE: decide S/L per group (otherwise everything kept goes to S, used for the S set itself).
+// finalize != 0: every element becomes its own group (ties are known to be final); no outputs.
+// baseS: device word holding the number of elements already in the S stream (nullptr = 0).
+template <bool ROUTE>
 __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, const u32 *__restrict__ idx,
                                                   const u32 *__restrict__ grp, const u32 *__restrict__ gst, u32 m,
-                                                  int finalize, u32 *__restrict__ rank, u32 *__restrict__ idx_out,
-                                                  u32 *__restrict__ grp_out, u32 *__restrict__ gst_out,
-                                                  u64 *__restrict__ status, RerankCounters *__restrict__ ctr)
+                                                  int finalize, u32 *__restrict__ rank, LiveOut outS,
+                                                  const u32 *__restrict__ baseS, LiveOut outL,
+                                                  u64 *__restrict__ statusA, u64 *__restrict__ statusB,
+                                                  RerankCounters *__restrict__ ctr)
 {
-    __shared__ u8 s_head[RR_TILE + 1];
-    __shared__ u32 s_wh[RR_NT / 32], s_wk[RR_NT / 32];
-    __shared__ u32 s_tile, s_exh, s_exk;
+    __shared__ u8 s_hb[RR_NT + 8];  // head flags of the tile, 8 slots per byte, + the slot after the tile
+    __shared__ u32 s_wh[RR_NT / 32], s_ws[RR_NT / 32], s_wl[RR_NT / 32];
+    __shared__ u32 s_tile, s_exh, s_exs, s_exl;
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
+    if (tid < 8) s_hb[RR_NT + tid] = 0;
     __syncthreads();
     const u32 tile = s_tile, base = tile * RR_TILE;
-    const u32 cnt = min((u32)RR_TILE, m - base);
+    const u32 j0 = base + tid * RR_IPT;
 
-    // head flags for positions base .. base+cnt (one past the tile), coalesced
-    for (u32 s = tid; s <= cnt; s += RR_NT) {
-        const u32 j = base + s;
-        u8 h = 1;
-        if (j < m && !finalize) {
-            h = (__ldg(gst + j) == j);
-            if (!h) h = ldg_stream_u64(keys + j) != __ldg(keys + j - 1);
+    // ---- my 8 slots, loaded up front (vector loads when the whole stretch is in range)
+    u32 vi[RR_IPT], vg[RR_IPT], vs[RR_IPT];
+    u64 vk[RR_IPT];
+    const bool full = (u64)j0 + RR_IPT <= m;
+    if (full) {
+#pragma unroll
+        for (int q = 0; q < RR_IPT / 4; q++) {
+            const uint4 a = ldg_stream_u4((const uint4 *)(idx + j0) + q);
+            const uint4 b = ldg_stream_u4((const uint4 *)(grp + j0) + q);
+            const uint4 c = ldg_stream_u4((const uint4 *)(gst + j0) + q);
+            vi[4 * q] = a.x; vi[4 * q + 1] = a.y; vi[4 * q + 2] = a.z; vi[4 * q + 3] = a.w;
+            vg[4 * q] = b.x; vg[4 * q + 1] = b.y; vg[4 * q + 2] = b.z; vg[4 * q + 3] = b.w;
+            vs[4 * q] = c.x; vs[4 * q + 1] = c.y; vs[4 * q + 2] = c.z; vs[4 * q + 3] = c.w;
         }
-        s_head[s] = h;
+        if (!finalize) {
+#pragma unroll
+            for (int q = 0; q < RR_IPT / 2; q++) {
+                const uint4 a = __ldg((const uint4 *)(keys + j0) + q);
+                vk[2 * q] = ((u64)a.y << 32) | a.x;
+                vk[2 * q + 1] = ((u64)a.w << 32) | a.z;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < RR_IPT; q++) {
+            const bool in = (u64)j0 + q < m;
+            vi[q] = in ? idx[j0 + q] : 0;
+            vg[q] = in ? grp[j0 + q] : 0;
+            vs[q] = in ? gst[j0 + q] : 0;
+            vk[q] = (in && !finalize) ? keys[j0 + q] : 0;
+        }
     }
+    const u32 mine = (j0 >= m) ? 0u : min((u32)RR_IPT, m - j0);  // slots of mine that exist
+    // head flags of my slots and of the slot right after them
+    u32 hbits = 0;  // bit q = slot j0+q starts a group; bit 8 = slot j0+8 does (or is past the end)
+    if (finalize) {
+        hbits = 0x1ffu;
+    } else {
+        u64 prevk = 0;
+        if (j0 > 0 && j0 < m) prevk = __ldg(keys + j0 - 1);
+#pragma unroll
+        for (int q = 0; q < RR_IPT; q++) {
+            if ((u32)q < mine) {
+                const bool h = (vs[q] == j0 + q) || (vk[q] != (q ? vk[q - 1] : prevk));
+                hbits |= (u32)h << q;
+            }
+        }
+        const u64 jn = (u64)j0 + RR_IPT;
+        bool hn = true;
+        if (jn < m) hn = (__ldg(gst + jn) == (u32)jn) || (__ldg(keys + jn) != vk[RR_IPT - 1]);
+        hbits |= (u32)hn << RR_IPT;
+    }
+    if (mine < RR_IPT) hbits |= 1u << mine;  // the slot after the last live slot acts as a head
+    s_hb[tid] = (u8)hbits;
+    if (tid == RR_NT - 1) s_hb[RR_NT] = (u8)(hbits >> RR_IPT);
     __syncthreads();
 
-    // thread owns RR_IPT consecutive slots
-    const u32 s0 = tid * RR_IPT;
-    u32 lasth = 0, nkeep = 0, nhead = 0, nkhead = 0;  // lasth = position+1 of the last head in my slots
-    u32 hbits = 0, kbits = 0;
+    // ---- per slot: keep?  which stream?
+    // next head strictly after tile slot hs, looked for in the following 32 slots
+    auto group_small = [&](u32 hs) -> bool {
+        const u32 b0 = hs + 1;
+        const u32 by = b0 >> 3;
+        u64 wbits = 0;
 #pragma unroll
-    for (int q = 0; q < RR_IPT; q++) {
-        const u32 s = s0 + q;
-        if (s < cnt) {
-            const u32 h = s_head[s], hn = s_head[s + 1];
-            const u32 keep = !(h && hn);
-            hbits |= h << q;
-            kbits |= keep << q;
-            if (h) { lasth = base + s + 1; nhead++; nkhead += keep; }
-            nkeep += keep;
+        for (int t = 0; t < 6; t++) {
+            const u32 bi = by + t;
+            wbits |= (u64)(bi <= RR_NT ? s_hb[bi] : 0) << (8 * t);
+        }
+        const u32 w32 = (u32)(wbits >> (b0 & 7));
+        return w32 != 0;  // a head within 32 slots: the group has at most 32 members
+    };
+    u32 kbits = 0, sbits = 0;  // keep, keep-in-S
+    u32 lasth = 0, nS = 0, nL = 0, nhead = 0, nkhead = 0;
+    {
+        // the group my first slot continues: its head is an earlier slot of this tile (or outside it)
+        int route = -1;  // -1 unknown yet, 0 = L, 1 = S
+#pragma unroll
+        for (int q = 0; q < RR_IPT; q++) {
+            if ((u32)q < mine) {
+                const u32 h = (hbits >> q) & 1, hn = (hbits >> (q + 1)) & 1;
+                const u32 keep = !(h && hn);
+                if (h) {
+                    lasth = j0 + q + 1;
+                    nhead++;
+                    nkhead += keep;
+                    route = -1;
+                }
+                if (keep) {
+                    if (!ROUTE) {
+                        route = 1;
+                    } else if (route < 0) {
+                        // find my group's head inside the tile
+                        int hs = (int)(tid * RR_IPT) + q;
+                        if (!h) {
+                            // walk back over the head bytes (at most 32 slots matter)
+                            int found = -1;
+                            for (int back = 1; back <= RR_SMALL && hs - back >= 0; back++) {
+                                const int sl = hs - back;
+                                if ((s_hb[sl >> 3] >> (sl & 7)) & 1) { found = sl; break; }
+                            }
+                            hs = found;
+                        }
+                        route = (hs >= 0 && group_small((u32)hs)) ? 1 : 0;
+                    }
+                    kbits |= 1u << q;
+                    if (route == 1) { sbits |= 1u << q; nS++; } else nL++;
+                }
+            }
         }
     }
-    // block-wide inclusive scans of (max lasth, sum nkeep)
-    const u32 ih = warp_incl_max(lasth), ik = warp_incl_sum(nkeep);
-    if (lane == 31) { s_wh[warp] = ih; s_wk[warp] = ik; }
+
+    // ---- block-wide scans of (max lasth, sum nS, sum nL)
+    const u32 ih = warp_incl_max(lasth), is = warp_incl_sum(nS), il = warp_incl_sum(nL);
+    if (lane == 31) { s_wh[warp] = ih; s_ws[warp] = is; s_wl[warp] = il; }
     const u32 th = warp_sum(nhead), tkh = warp_sum(nkhead);
     if (lane == 0 && (th | tkh)) { atomicAdd(&ctr->heads, th); atomicAdd(&ctr->kheads, tkh); }
     __syncthreads();
-    u32 offh = 0, offk = 0, toth = 0, totk = 0;
+    u32 offh = 0, offs = 0, offl = 0, toth = 0, tots = 0, totl = 0;
 #pragma unroll
     for (int w = 0; w < RR_NT / 32; w++) {
-        if (w < (int)warp) { offh = max(offh, s_wh[w]); offk += s_wk[w]; }
+        if (w < (int)warp) { offh = max(offh, s_wh[w]); offs += s_ws[w]; offl += s_wl[w]; }
         toth = max(toth, s_wh[w]);
-        totk += s_wk[w];
+        tots += s_ws[w];
+        totl += s_wl[w];
     }
 
-    // decoupled look-back on (max, sum), by warp 0
+    // ---- decoupled look-back on (max, sum, sum), by warp 0
     if (warp == 0) {
-        u32 exh = 0, exk = 0;
+        u32 exh = 0, exs = 0, exl = 0;
         if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(status, rr_pack(RR_FLAG_PREFIX, toth, totk));
+            if (lane == 0) {
+                st_relaxed_u64(statusB, rr_packB(RR_FLAG_PREFIX, totl));
+                st_relaxed_u64(statusA, rr_packA(RR_FLAG_PREFIX, toth, tots));
+            }
         } else {
-            if (lane == 0) st_relaxed_u64(status + tile, rr_pack(RR_FLAG_AGG, toth, totk));
+            if (lane == 0) {
+                st_relaxed_u64(statusB + tile, rr_packB(RR_FLAG_AGG, totl));
+                st_relaxed_u64(statusA + tile, rr_packA(RR_FLAG_AGG, toth, tots));
+            }
             int t = (int)tile - 1;
             for (;;) {
                 const int q = t - (int)lane;
-                const u64 v = (q >= 0) ? ld_relaxed_u64(status + q) : rr_pack(RR_FLAG_PREFIX, 0, 0);
-                const u32 flag = (u32)(v >> 62);
+                const u64 va = (q >= 0) ? ld_relaxed_u64(statusA + q) : rr_packA(RR_FLAG_PREFIX, 0, 0);
+                const u64 vb = (q >= 0) ? ld_relaxed_u64(statusB + q) : rr_packB(RR_FLAG_PREFIX, 0);
+                const u32 fa = (u32)(va >> 62), fb = (u32)(vb >> 62);
+                // a tile counts once both of its words carry the same kind of flag
+                const u32 flag = (fa == fb) ? fa : 0u;
                 const u32 empties = __ballot_sync(FULL_MASK, flag == 0);
                 const u32 prefixes = __ballot_sync(FULL_MASK, flag == (u32)RR_FLAG_PREFIX);
-                u32 take;  // lanes whose words are folded in
+                u32 take;
                 if (prefixes) {
                     const u32 fp = __ffs(prefixes) - 1;
                     take = (fp == 31) ? FULL_MASK : ((2u << fp) - 1);
@@ -242,53 +355,120 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
                     if (empties) continue;
                     take = FULL_MASK;
                 }
-                const bool mine = (take >> lane) & 1;
-                const u32 h = mine ? (u32)((v >> 31) & 0x7fffffffu) : 0;
-                const u32 kq = mine ? (u32)(v & 0x7fffffffu) : 0;
-                exh = max(exh, warp_max(h));
-                exk += warp_sum(kq);
+                const bool on = (take >> lane) & 1;
+                exh = max(exh, warp_max(on ? (u32)((va >> 31) & 0x7fffffffu) : 0u));
+                exs += warp_sum(on ? (u32)(va & 0x7fffffffu) : 0u);
+                exl += warp_sum(on ? (u32)vb : 0u);
                 if (prefixes) break;
                 t -= 32;
             }
-            if (lane == 0) st_relaxed_u64(status + tile, rr_pack(RR_FLAG_PREFIX, max(exh, toth), exk + totk));
+            if (lane == 0) {
+                st_relaxed_u64(statusB + tile, rr_packB(RR_FLAG_PREFIX, exl + totl));
+                st_relaxed_u64(statusA + tile, rr_packA(RR_FLAG_PREFIX, max(exh, toth), exs + tots));
+            }
         }
         if (lane == 0) {
-            s_exh = exh;
-            s_exk = exk;
-            if (totk) atomicAdd(&ctr->kept, totk);
+            s_exh = exh; s_exs = exs; s_exl = exl;
+            if (tots) atomicAdd(&ctr->keptS, tots);
+            if (totl) atomicAdd(&ctr->keptL, totl);
         }
     }
     __syncthreads();
-    const u32 exh = s_exh, exk = s_exk;
 
-    // exclusive state in front of my first slot
-    {
-        // exclusive (over threads) versions of the warp scans
-        u32 eh = __shfl_up_sync(FULL_MASK, ih, 1);
-        u32 ek = __shfl_up_sync(FULL_MASK, ik, 1);
-        if (lane == 0) { eh = 0; ek = 0; }
-        u32 curh = max(exh, max(offh, eh));
-        u32 curk = exk + offk + ek;
+    // ---- outputs
+    u32 eh = __shfl_up_sync(FULL_MASK, ih, 1);
+    u32 es = __shfl_up_sync(FULL_MASK, is, 1);
+    u32 el = __shfl_up_sync(FULL_MASK, il, 1);
+    if (lane == 0) { eh = 0; es = 0; el = 0; }
+    u32 curh = max(s_exh, max(offh, eh));
+    u32 curs = (baseS ? *baseS : 0u) + s_exs + offs + es;
+    u32 curl = s_exl + offl + el;
 #pragma unroll
-        for (int q = 0; q < RR_IPT; q++) {
-            const u32 s = s0 + q;
-            if (s < cnt) {
-                const u32 j = base + s;
-                if ((hbits >> q) & 1) curh = j + 1;
-                const u32 jh = curh - 1;  // every slot has a head at or before it (slot gst[j] is one)
-                const u32 g = __ldg(grp + j), gs = __ldg(gst + j);
-                const u32 nr = g + (jh - gs);
-                const u32 i = __ldg(idx + j);
-                if (nr != g) rank[i] = nr;
-                if ((kbits >> q) & 1) {
-                    idx_out[curk] = i;
-                    grp_out[curk] = nr;
-                    gst_out[curk] = curk - (j - jh);
-                    curk++;
+    for (int q = 0; q < RR_IPT; q++) {
+        if ((u32)q < mine) {
+            const u32 j = j0 + q;
+            if ((hbits >> q) & 1) curh = j + 1;
+            const u32 jh = curh - 1;  // every slot has a head at or before it (slot gst[j] is one)
+            const u32 nr = vg[q] + (jh - vs[q]);
+            if (nr != vg[q]) rank[vi[q]] = nr;
+            if ((kbits >> q) & 1) {
+                if ((sbits >> q) & 1) {
+                    outS.idx[curs] = vi[q];
+                    outS.grp[curs] = nr;
+                    outS.gst[curs] = curs - (j - jh);
+                    curs++;
+                } else {
+                    outL.idx[curl] = vi[q];
+                    outL.grp[curl] = nr;
+                    outL.gst[curl] = curl - (j - jh);
+                    curl++;
                 }
             }
         }
     }
+}
+
+// ---- local sort: one doubling round when every live group has at most 32 members ---------------
+// Warp w owns the whole groups between the group holding live slot 32w and the group holding
+// slot 32w+32 (at most 63 slots): gather key2 = rank[succ^k(idx)], order the slots by
+// (group, key2) by counting, write keys / idx in the layout the radix path would have produced.
+__global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *__restrict__ idx, const u32 *__restrict__ gst,
+                                                         u32 m, const u32 *__restrict__ rank,
+                                                         const u32 *__restrict__ FS, const u32 *__restrict__ cidx,
+                                                         u32 k, u32 kb, u32 n, int linear,
+                                                         u64 *__restrict__ keys_out, u32 *__restrict__ idx_out)
+{
+    const u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 lane = lane_id();
+    if ((u64)w * 32 >= m) return;
+    const u32 lo = __ldg(gst + w * 32);
+    const u32 hi = ((u64)(w + 1) * 32 < m) ? __ldg(gst + (w + 1) * 32) : m;
+    const u32 cnt = hi - lo;  // 1 .. 63
+    u64 key[2];
+    u32 pay[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const u32 t = lane + 32 * h;
+        key[h] = ~0ull;
+        pay[h] = 0;
+        if (t < cnt) {
+            const u32 j = lo + t;
+            const u32 i = ldg_stream_u32(idx + j);
+            const u32 g = ldg_stream_u32(gst + j);
+            u32 r;
+            if (linear) {
+                const u64 tt = (u64)i + k;
+                r = (tt < n) ? __ldg(rank + (u32)tt) + 1 : 0;
+            } else {
+                const u32 f = factor_of(FS, cidx, i);
+                const u32 s = __ldg(FS + f), len = __ldg(FS + f + 1) - s;
+                u32 o = i - s;
+                if (len > 1) {
+                    o += (k < len) ? k : k % len;
+                    if (o >= len) o -= len;
+                }
+                r = __ldg(rank + s + o);
+            }
+            key[h] = ((u64)g << kb) | (u64)r;
+            pay[h] = i;
+        }
+    }
+    // position = number of slots that order before mine (ties broken by slot number)
+    u32 pos[2] = {0, 0};
+    for (u32 t = 0; t < cnt; t++) {
+        const u64 other = __shfl_sync(FULL_MASK, (t < 32) ? key[0] : key[1], t & 31);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 me = lane + 32 * h;
+            pos[h] += (other < key[h]) || (other == key[h] && t < me);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+        if (lane + 32 * h < cnt) {
+            keys_out[lo + pos[h]] = key[h];
+            idx_out[lo + pos[h]] = pay[h];
+        }
 }
 
 // ---- emit -----------------------------------------------------------------------------------------

@@ -96,6 +96,7 @@ typedef struct {
     int    initial_depth;       /* forward: symbols in the initial key (k0)             */
     int    rounds;              /* forward: doubling rounds after the initial sort      */
     int    radix_passes;        /* forward: onesweep passes launched                    */
+    int    local_rounds;        /* forward: rounds served by the warp-local sort        */
     long   live_sum;            /* forward: sum over rounds of live elements            */
     long   splitters;           /* inverse: sublists                                    */
     long   unreached;           /* inverse: elements ranked by the self-walk fallback   */
@@ -121,7 +122,8 @@ const char *bwts_b200_version(void);
 
 /* Test hooks: override tuning constants so that small inputs exercise the multi-tile /
  * multi-chunk paths.  key: 0 = Lyndon chunk bytes (>= 1), 1 = inverse splitter shift
- * (density 2^-(32-shift), 20..31), 2 = onesweep tile shape (0..3).  value 0 = default.       */
+ * (density 2^-(32-shift), 20..31), 2 = onesweep tile shape (0..3), 3 = disable the
+ * warp-local sort path (1).  value 0 = default.       */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

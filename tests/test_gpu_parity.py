@@ -220,3 +220,19 @@ def test_context_reuse_across_sizes(ctx, oracle, gen):
         y = ctx.forward_host(x)
         assert y == oracle.forward(x), (kind, seed, n)
         assert ctx.inverse_host(y) == x, (kind, seed, n)
+
+
+def test_local_sort_path_and_radix_only_path_agree(bwts, ctx, oracle, gen):
+    """forward with the warp-local sort of small groups (default) and with the global radix
+    path only (tune 3 = 1) must both equal the oracle"""
+    cases = [gen.make("dna", 77, 1_500_000), gen.make("text", 78, 1_000_000), gen.make("tiled", 79, 1_300_000),
+             helpers.families(70_000)["ww"], helpers.families(70_000)["runs"], helpers.fibonacci_word(200_000)]
+    for x in cases:
+        want = oracle.forward(x)
+        bwts.tune(3, 1)
+        a = ctx.forward_host(x)
+        ra = ctx.stats()["local_rounds"]
+        bwts.tune(3, 0)
+        b = ctx.forward_host(x)
+        assert a == want and b == want
+        assert ra == 0
