@@ -34,7 +34,28 @@ WORKLOADS = {
     "C3": ("tiled", 3, 256 << 20, "C3: 256 MiB 64 KiB-tiled text, one substitution per MiB"),
     "C4": ("dna", 4, 1 << 30, "C4: 1 GiB DNA (ACGT) with copied segments"),
     "C3F": ("fibonacci", 0, 256 << 20, "C3 stress: 256 MiB Fibonacci word"),
+    # C5: a multi-block file of 8 x 256 MiB independent blocks (seeds 50..57) dealt over the ranks
+    "C5": ("text", 50, 256 << 20, "C5: multi-block file, 8 x 256 MiB order-2 Markov text blocks"),
 }
+C5_BLOCKS = 8
+
+
+def block_owner(block, ndev):
+    """Round-robin dealing of independent blocks, the same rule as bwts_b200_*_blocks (run_blocks)."""
+    return block % ndev
+
+
+def plan_blocks(workload, rank, world):
+    """(generator kind, seed, bytes) of every block this rank transforms in one step.
+    C1..C4: one block per rank (weak scaling).  C5: 8 fixed blocks dealt round-robin (strong)."""
+    kind, seed, n, _ = WORKLOADS[workload]
+    if workload == "C5":
+        return [(kind, seed + b, n) for b in range(C5_BLOCKS) if block_owner(b, world) == rank]
+    return [(kind, seed + 100 * rank, n)]
+
+
+def total_blocks(workload, world):
+    return C5_BLOCKS if workload == "C5" else world
 DOMINANT = "onesweep_pass"
 
 
@@ -154,9 +175,11 @@ def run_reference_arm(args, rank, world):
     while sample * 2 <= min(n, budget):
         sample *= 2
     nproc = os.cpu_count() or 1
-    blocks = world  # the GPU arm gives every rank one block; the CPU arm runs them side by side
+    # the same blocks the GPU arm transforms in one step, run side by side on the host cores
+    all_blocks = [blk for r in range(world) for blk in plan_blocks(args.workload, r, world)]
+    datas = [make_input(k_, s_, n_)[:sample] for k_, s_, n_ in all_blocks]
+    blocks = len(datas)
     conc = min(blocks, nproc)
-    datas = [make_input(kind_name, seed + 100 * b, n)[:sample] for b in range(blocks)]
 
     def one_step():
         t0 = time.perf_counter()
@@ -180,8 +203,10 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": "bwts_round_trip_throughput", "value": value, "unit": "MB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": desc + ", forward + inverse round trip", "bytes_per_gpu": n, "sample_bytes": sample},
+        "higher_is_better": True, "scaling": "strong" if args.workload == "C5" else "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc + ", forward + inverse round trip", "bytes_per_gpu": n * blocks // world,
+                   "blocks": blocks, "sample_bytes": sample},
         "cpu_baseline": {"value": value, "unit": "MB/s", "cores": conc, "kind": kind, "sample": sample_desc},
         "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -205,21 +230,24 @@ def run_gpu_arm(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     kind_name, seed, n, desc = WORKLOADS[args.workload]
+    plan = plan_blocks(args.workload, rank, world)
     if args.bytes:
         n = args.bytes
-    data = make_input(kind_name, seed + 100 * rank, n)
-
+        plan = [(k_, s_, n) for k_, s_, _ in plan]
     for kv in args.tune:
         k, v = kv.split(":")
         bwts.tune(int(k), int(v))
     ctx = bwts.Context(local_rank)
     ctx.reserve(n)
-    host_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
-    host_mid = torch.empty(n, dtype=torch.uint8).pin_memory()
-    host_back = torch.empty(n, dtype=torch.uint8).pin_memory()
-    d_in = host_in.to(dev)
-    d_mid = torch.empty_like(d_in)
-    d_back = torch.empty_like(d_in)
+    blocks = []
+    for k_, s_, n_ in plan:
+        data = make_input(k_, s_, n_)
+        host_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+        blocks.append({"data": data, "host_in": host_in, "host_mid": torch.empty(n_, dtype=torch.uint8).pin_memory(),
+                       "host_back": torch.empty(n_, dtype=torch.uint8).pin_memory(), "d_in": host_in.to(dev),
+                       "d_mid": torch.empty(n_, dtype=torch.uint8, device=dev),
+                       "d_back": torch.empty(n_, dtype=torch.uint8, device=dev), "n": n_})
+    my_bytes = sum(b["n"] for b in blocks)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
     sh = stream.cuda_stream
@@ -237,26 +265,34 @@ def run_gpu_arm(args, rank, local_rank, world):
             a["launches"] += c["launches"]; a["ms"] += c["ms"]; a["bytes"] += c["bytes"]
 
     def device_step(acc=None):
-        flush.zero_()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e2 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        ctx.forward_device(d_in.data_ptr(), n, d_mid.data_ptr(), sh)
-        sf = ctx.stats()
-        e1.record(stream)
-        ctx.inverse_device(d_mid.data_ptr(), n, d_back.data_ptr(), sh)
-        si = ctx.stats()
-        e2.record(stream)
-        if acc is not None:
-            absorb(sf, acc); absorb(si, acc)
-        return e0, e1, e2, sf, si
+        """forward + inverse of every block this rank owns; returns (fwd_ms events, inv_ms events, launches)"""
+        out = []
+        for b in blocks:
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e2 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.forward_device(b["d_in"].data_ptr(), b["n"], b["d_mid"].data_ptr(), sh)
+            sf = ctx.stats()
+            e1.record(stream)
+            ctx.inverse_device(b["d_mid"].data_ptr(), b["n"], b["d_back"].data_ptr(), sh)
+            si = ctx.stats()
+            e2.record(stream)
+            if acc is not None:
+                absorb(sf, acc); absorb(si, acc)
+            out.append((e0, e1, e2, sf, si))
+        return out
+
+    def check_round_trip():
+        for b in blocks:
+            assert torch.equal(b["d_back"], b["d_in"]), "round trip lost data"
 
     # ---- warm-up (also the correctness gate of the bench itself)
-    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+    for _ in range(args.warmup):
         device_step()
     torch.cuda.synchronize(dev)
     if args.warmup:
-        assert torch.equal(d_back, d_in), "round trip lost data"
+        check_round_trip()
 
     # ---- timed region: exactly K steps, device resident
     sampler = ClockSampler(local_rank)
@@ -266,11 +302,12 @@ def run_gpu_arm(args, rank, local_rank, world):
     t_begin.record(stream)
     evs = []
     launches = 0
+    last_f = last_i = None
     for _ in range(args.steps):
-        e0, e1, e2, sf, si = device_step(agg)
-        launches += sf["launches"] + si["launches"]
-        evs.append((e0, e1, e2))
-        last_f, last_i = sf, si
+        for e0, e1, e2, sf, si in device_step(agg):
+            launches += sf["launches"] + si["launches"]
+            evs.append((e0, e1, e2))
+            last_f, last_i = sf, si
     t_end.record(stream)
     torch.cuda.synchronize(dev)
     clocks = sampler.stop()
@@ -278,18 +315,19 @@ def run_gpu_arm(args, rank, local_rank, world):
     total_ms = t_begin.elapsed_time(t_end)
     fwd_ms = sum(a.elapsed_time(b) for a, b, _ in evs) / args.steps
     inv_ms = sum(b.elapsed_time(c) for _, b, c in evs) / args.steps
-    assert torch.equal(d_back, d_in), "round trip lost data"
+    check_round_trip()
 
     # ---- end to end: the host-buffer C-ABI call, pinned host memory, both copies inside
     def e2e_step():
         t0 = time.perf_counter()
-        ctx.forward_host_ptr(host_in.data_ptr(), n, host_mid.data_ptr())
-        sf = ctx.stats()
-        ctx.inverse_host_ptr(host_mid.data_ptr(), n, host_back.data_ptr())
-        si = ctx.stats()
-        wall = time.perf_counter() - t0
-        dev_ms = sum(s["h2d_ms"] + s["total_ms"] + s["d2h_ms"] for s in (sf, si))
-        return wall * 1e3, dev_ms
+        dev_ms = 0.0
+        for b in blocks:
+            ctx.forward_host_ptr(b["host_in"].data_ptr(), b["n"], b["host_mid"].data_ptr())
+            sf = ctx.stats()
+            ctx.inverse_host_ptr(b["host_mid"].data_ptr(), b["n"], b["host_back"].data_ptr())
+            si = ctx.stats()
+            dev_ms += sum(s["h2d_ms"] + s["total_ms"] + s["d2h_ms"] for s in (sf, si))
+        return (time.perf_counter() - t0) * 1e3, dev_ms
 
     for _ in range(min(args.warmup, 2)):
         e2e_step()
@@ -298,13 +336,18 @@ def run_gpu_arm(args, rank, local_rank, world):
     barrier()
     e2e_wall_ms = sum(w for w, _ in e2e) / args.steps
     e2e_dev_ms = sum(d for _, d in e2e) / args.steps
-    assert bytes(host_back.numpy()[:4096]) == data[:4096] and torch.equal(host_back, host_in), "e2e round trip lost data"
+    for b in blocks:
+        assert torch.equal(b["host_back"], b["host_in"]), "e2e round trip lost data"
+    data, d_mid = blocks[0]["data"], blocks[0]["d_mid"]
 
-    # ---- max over ranks
+    # ---- max over ranks (times), sum over ranks (bytes)
     t = torch.tensor([total_ms, fwd_ms, inv_ms, e2e_wall_ms, e2e_dev_ms], dtype=torch.float64, device=dev)
+    nb = torch.tensor([float(my_bytes)], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nb, op=dist.ReduceOp.SUM)
     total_ms, fwd_ms, inv_ms, e2e_wall_ms, e2e_dev_ms = t.tolist()
+    job_bytes = nb.item()
     ms_per_step = total_ms / args.steps
 
     if rank == 0:
@@ -319,18 +362,20 @@ def run_gpu_arm(args, rank, local_rank, world):
             except Exception:
                 traffic = None
         line = {
-            "metric": "bwts_round_trip_throughput", "value": world * n / MB / (ms_per_step * 1e-3), "unit": "MB/s",
+            "metric": "bwts_round_trip_throughput", "value": job_bytes / MB / (ms_per_step * 1e-3), "unit": "MB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": desc + ", forward + inverse round trip", "bytes_per_gpu": n,
-                       "blocks": world, "l2": "flushed between steps (256 MiB device memset inside the timed loop)",
-                       "generator": f"bijective-bwt_b200/host/gen_input.c kind={kind_name} seed={seed}+100*rank",
-                       "parallelism": f"independent blocks x{world}, no collective"},
-            "forward_mbs": world * n / MB / (fwd_ms * 1e-3), "inverse_mbs": world * n / MB / (inv_ms * 1e-3),
+            "higher_is_better": True, "scaling": "strong" if args.workload == "C5" else "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": desc + ", forward + inverse round trip", "bytes_per_gpu": my_bytes,
+                       "blocks": total_blocks(args.workload, world), "l2": "flushed between steps (256 MiB device memset inside the timed loop)",
+                       "generator": f"bijective-bwt_b200/host/gen_input.c kind={kind_name} seed={seed}"
+                                    + ("+block" if args.workload == "C5" else "+100*rank"),
+                       "parallelism": f"independent blocks over {world} GPU(s), round-robin, no collective"},
+            "forward_mbs": job_bytes / MB / (fwd_ms * 1e-3), "inverse_mbs": job_bytes / MB / (inv_ms * 1e-3),
             "forward_ms": fwd_ms, "inverse_ms": inv_ms,
-            "e2e": {"value": world * n / MB / (e2e_dev_ms * 1e-3), "unit": "MB/s",
-                    "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 2 * n,
-                    "wall_value": world * n / MB / (e2e_wall_ms * 1e-3),
+            "e2e": {"value": job_bytes / MB / (e2e_dev_ms * 1e-3), "unit": "MB/s",
+                    "h2d_bytes_per_step": 2 * my_bytes, "d2h_bytes_per_step": 2 * my_bytes,
+                    "wall_value": job_bytes / MB / (e2e_wall_ms * 1e-3),
                     "how": "bwts_b200_forward_host + bwts_b200_inverse_host on pinned host buffers; CUDA events "
                            "from before the H2D copy to after the D2H copy (wall_value: host clock)"},
             "gpu_launches": launches,
