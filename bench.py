@@ -95,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -310,7 +310,6 @@ def run_gpu_arm(args, rank, local_rank, world):
             last_f, last_i = sf, si
     t_end.record(stream)
     torch.cuda.synchronize(dev)
-    clocks = sampler.stop()
     barrier()
     total_ms = t_begin.elapsed_time(t_end)
     fwd_ms = sum(a.elapsed_time(b) for a, b, _ in evs) / args.steps
@@ -333,6 +332,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         e2e_step()
     barrier()
     e2e = [e2e_step() for _ in range(args.steps)]
+    clocks = sampler.stop()  # sampled across both timed regions (device-resident and end-to-end)
     barrier()
     e2e_wall_ms = sum(w for w, _ in e2e) / args.steps
     e2e_dev_ms = sum(d for _, d in e2e) / args.steps
