@@ -192,10 +192,10 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
         CK(cudaGetLastError());                                                                           \
     } while (0)
         switch (g_tune_onesweep) {
-        case 1: OS_LAUNCH(512, 8, 2, 8); break;
-        case 2: OS_LAUNCH(512, 8, 2, 32); break;
-        case 3: OS_LAUNCH(256, 8, 4, 16); break;
-        default: OS_LAUNCH(512, 8, 2, 16); break;
+        case 1: OS_LAUNCH(512, 8, 2, 16); break;
+        case 2: OS_LAUNCH(512, 8, 2, 4); break;
+        case 3: OS_LAUNCH(256, 8, 4, 8); break;
+        default: OS_LAUNCH(512, 8, 2, 8); break;
         }
 #undef OS_LAUNCH
         sb.cur = b;
@@ -541,8 +541,8 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
                          (int)OsSmem<NT_, IPT_>::bytes);                                                         \
     cudaFuncSetAttribute(k_onesweep_pass<NT_, IPT_, MINB_, LB_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
     OS_ATTR(512, 8, 2, 8);
-    OS_ATTR(512, 8, 2, 32);
-    OS_ATTR(256, 8, 4, 16);
+    OS_ATTR(512, 8, 2, 4);
+    OS_ATTR(256, 8, 4, 8);
     OS_ATTR(512, 8, 2, 16);
 #undef OS_ATTR
     bwts_b200_ctx *ctx = new bwts_b200_ctx();
