@@ -310,8 +310,6 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     if (rc) return rc;
 
     CK(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
-    CK(cudaMemsetAsync(grp[0], 0, (size_t)n * 4, st));
-    CK(cudaMemsetAsync(gst[0], 0, (size_t)n * 4, st));
 
     // Two live sets.  L: groups of any size, sorted by the global radix path (sb, grp, gst).
     // S: groups of at most 32 members, sorted warp-locally (kS, vS, grpS, gstS).
@@ -339,11 +337,12 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             if (g_tune_local) {
                 LiveOut none = {nullptr, nullptr, nullptr};
                 LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<false>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
-                       grp[g], gst[g], mL, 0, rank, oL, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 1);
+                       first ? (const u32 *)nullptr : grp[g], gst[g], mL, 0, rank, oL, (const u32 *)nullptr, none,
+                       rr_statusA, rr_statusB, rrc + 1);
             } else {
                 LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<true>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
-                       grp[g], gst[g], mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL, rr_statusA, rr_statusB,
-                       rrc + 1);
+                       first ? (const u32 *)nullptr : grp[g], gst[g], mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL,
+                       rr_statusA, rr_statusB, rrc + 1);
             }
         }
         rc = readback(ctx, st, rrc, 2 * sizeof(RerankCounters));
@@ -424,7 +423,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
 
     // -- emit
     if (!linear) {
-        LAUNCH(KC_EMIT, 7.0 * n, k_emit, cdiv(n, 256), 256, dT, n, rank, flags, d_out);
+        // rank windows of 64 Mi slots: the scatter target of one launch stays resident in the 126 MB L2
+        const u32 win = 64u << 20;
+        for (u64 lo = 0; lo < n; lo += win) {
+            const u32 hi = (u32)min((u64)n, lo + win);
+            LAUNCH(KC_EMIT, (lo == 0 ? 7.0 : 4.0) * n, k_emit, cdiv(cdiv(n, 4), 256), 256, dT, n, rank, flags, d_out,
+                   (u32)lo, hi);
+        }
         LAUNCH(KC_EMIT, 10.0 * F, k_emit_heads, cdiv(F, 256), 256, dT, FS, F, rank, d_out);
     } else {
         LAUNCH(KC_EMIT, 8.0 * n, k_emit_sa, cdiv(n, 256), 256, rank, n, d_sa);
@@ -449,25 +454,25 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     u32 *tilehist = arena_take<u32>(ctx, (size_t)ntiles * 256);
     u32 *chunksum = arena_take<u32>(ctx, (size_t)nchunks * 256);
     u32 *prev = arena_take<u32>(ctx, n);
-    uint2 *rec = arena_take<uint2>(ctx, n);
+    u32 *sid = arena_take<u32>(ctx, n);
     u32 *len_at_min = arena_take<u32>(ctx, n);
     u32 *off = arena_take<u32>(ctx, n);
     uint2 *cyc = arena_take<uint2>(ctx, n);
     u32 *tilecnt = arena_take<u32>(ctx, max(nst, nsc) + 1);
-    u32 *small = arena_take<u32>(ctx, 64);
-    if (!tilehist || !chunksum || !prev || !rec || !len_at_min || !off || !cyc || !tilecnt || !small)
+    u32 *small = arena_take<u32>(ctx, 512);  // [0] ns, [2] visited total, [4] unreached, [6] cycles, [8] scan total, [64..320] C
+    if (!tilehist || !chunksum || !prev || !sid || !len_at_min || !off || !cyc || !tilecnt || !small)
         return BWTS_B200_EINTERNAL;
+    u32 *Ctab = small + 64;
     CK(cudaMemsetAsync(small, 0, 64 * sizeof(u32), st));
 
     // -- LF map
     LAUNCH(KC_INV_HIST, 1.0 * n, k_inv_tile_hist, ntiles, INV_NT, dB, n, tilehist);
     LAUNCH(KC_INV_SCAN, 1024.0 * ntiles, k_inv_colsum, nchunks, 256, tilehist, ntiles, chunksum);
-    LAUNCH(KC_INV_SCAN, 0, k_inv_chunk_scan, 1, 256, chunksum, nchunks);
+    LAUNCH(KC_INV_SCAN, 0, k_inv_chunk_scan, 1, 256, chunksum, nchunks, Ctab);
     LAUNCH(KC_INV_SCAN, 2048.0 * ntiles, k_inv_tile_base, nchunks, 256, tilehist, ntiles, chunksum);
     LAUNCH(KC_INV_LF, 5.0 * n, k_inv_lf_rank, ntiles, INV_NT, dB, n, tilehist, prev);
 
     // -- splitters
-    CK(cudaMemsetAsync(rec, 0xff, (size_t)n * sizeof(uint2), st));
     CK(cudaMemsetAsync(len_at_min, 0, (size_t)n * 4, st));
     LAUNCH(KC_INV_WALK, 0, k_inv_spl_count, nst, 256, n, shift, tilecnt);
     LAUNCH(KC_INV_SCAN, 8.0 * nst, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, nst, small + 0);
@@ -482,8 +487,10 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     uint2 *minfo = arena_take<uint2>(ctx, ns);
     uint4 *srec = arena_take<uint4>(ctx, ns);
     if (!spl || !jm[0] || !jm[1] || !jm[2] || !pv[0] || !pv[1] || !wlen || !minfo || !srec) return BWTS_B200_EINTERNAL;
-    LAUNCH(KC_INV_WALK, 12.0 * ns, k_inv_spl_write, nst, 256, n, shift, tilecnt, spl, rec);
-    LAUNCH(KC_INV_WALK, 12.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, rec, jm[0], wlen, minfo);
+    LAUNCH(KC_INV_WALK, 8.0 * ns, k_inv_spl_write, nst, 256, n, shift, tilecnt, spl, sid);
+    // first walk: 4 B read per element
+    LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
+           (u32 *)nullptr, small + 2);
 
     // -- reduced list: cycle minimum, then distance to the sublist holding it
     const int R = bit_length((u64)ns - 1) + 1;
@@ -502,7 +509,23 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
         pc ^= 1;
     }
     LAUNCH(KC_INV_JUMP, 24.0 * ns, k_inv_origin_publish, gs, 256, jmR, pv[pc], minfo, ns, len_at_min, cyc);
-    LAUNCH(KC_INV_WALK, 8.0 * n, k_inv_self_walk, cdiv(n, 256), 256, prev, n, rec, len_at_min, small + 4);
+
+    // -- did the walks reach every element?  (they do unless a cycle holds no splitter)
+    rc = readback(ctx, st, small + 2, 4);
+    if (rc) return rc;
+    const u32 reached = ctx->h_small[0];
+    u32 *visited = nullptr;
+    uint2 *urec = nullptr;
+    if (reached != n) {
+        visited = arena_take<u32>(ctx, (size_t)(n >> 5) + 2);
+        urec = arena_take<uint2>(ctx, n);
+        if (!visited || !urec) return BWTS_B200_EINTERNAL;
+        CK(cudaMemsetAsync(visited, 0, ((size_t)(n >> 5) + 2) * 4, st));
+        LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
+               visited, (u32 *)nullptr);
+        LAUNCH(KC_INV_WALK, 12.0 * (n - reached), k_inv_self_walk, cdiv(n, 256), 256, prev, n, visited, urec,
+               len_at_min, small + 4);
+    }
 
     // -- offsets of the cycles, in order of ascending smallest index
     LAUNCH(KC_INV_SCAN, 4.0 * n, k_tile_sum_u32, nsc, 256, len_at_min, n, tilecnt);
@@ -510,9 +533,12 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     LAUNCH(KC_INV_SCAN, 8.0 * n, k_tile_scan_apply_u32, nsc, 256, len_at_min, off, n, tilecnt);
     LAUNCH(KC_INV_SCAN, 4.0 * n, k_inv_count_cycles, min(cdiv(n, 256), 148u * 8u), 256, len_at_min, n, small + 6);
 
-    // -- placement
+    // -- placement: second walk writes the bytes at descending consecutive positions
     LAUNCH(KC_INV_PLACE, 44.0 * ns, k_inv_spl_record, gs, 256, jmR, pv[pc], cyc, off, ns, srec);
-    LAUNCH(KC_INV_PLACE, 14.0 * n, k_inv_place, cdiv(n, 256), 256, dB, n, rec, srec, off, d_out);
+    LAUNCH(KC_INV_PLACE, 5.0 * n, k_inv_walk_place, cdiv(ns, 128), 128, prev, n, shift, spl, ns, srec, Ctab, d_out);
+    if (visited)
+        LAUNCH(KC_INV_PLACE, 14.0 * (n - reached), k_inv_place_unreached, cdiv(n, 256), 256, dB, n, visited, urec, off,
+               d_out);
 
     rc = readback(ctx, st, small, 40);
     if (rc) return rc;

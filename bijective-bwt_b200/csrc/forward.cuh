@@ -175,6 +175,8 @@ struct LiveOut {  // one compaction stream
     u32 *idx, *grp, *gst;
 };
 
+// grp == nullptr (with gst ignored): both arrays are all zero -- the first re-rank after the
+// initial sort, where the whole text is one group of rank 0 starting at slot 0.
 // ROUTE: decide S/L per group (otherwise everything kept goes to S, used for the S set itself).
 // finalize != 0: every element becomes its own group (ties are known to be final); no outputs.
 // baseS: device word holding the number of elements already in the S stream (nullptr = 0).
@@ -205,8 +207,9 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
 #pragma unroll
         for (int q = 0; q < RR_IPT / 4; q++) {
             const uint4 a = ldg_stream_u4((const uint4 *)(idx + j0) + q);
-            const uint4 b = ldg_stream_u4((const uint4 *)(grp + j0) + q);
-            const uint4 c = ldg_stream_u4((const uint4 *)(gst + j0) + q);
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 b = grp ? ldg_stream_u4((const uint4 *)(grp + j0) + q) : z4;
+            const uint4 c = grp ? ldg_stream_u4((const uint4 *)(gst + j0) + q) : z4;
             vi[4 * q] = a.x; vi[4 * q + 1] = a.y; vi[4 * q + 2] = a.z; vi[4 * q + 3] = a.w;
             vg[4 * q] = b.x; vg[4 * q + 1] = b.y; vg[4 * q + 2] = b.z; vg[4 * q + 3] = b.w;
             vs[4 * q] = c.x; vs[4 * q + 1] = c.y; vs[4 * q + 2] = c.z; vs[4 * q + 3] = c.w;
@@ -224,8 +227,8 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
         for (int q = 0; q < RR_IPT; q++) {
             const bool in = (u64)j0 + q < m;
             vi[q] = in ? idx[j0 + q] : 0;
-            vg[q] = in ? grp[j0 + q] : 0;
-            vs[q] = in ? gst[j0 + q] : 0;
+            vg[q] = (in && grp) ? grp[j0 + q] : 0;
+            vs[q] = (in && grp) ? gst[j0 + q] : 0;
             vk[q] = (in && !finalize) ? keys[j0 + q] : 0;
         }
     }
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
         }
         const u64 jn = (u64)j0 + RR_IPT;
         bool hn = true;
-        if (jn < m) hn = (__ldg(gst + jn) == (u32)jn) || (__ldg(keys + jn) != vk[RR_IPT - 1]);
+        if (jn < m) hn = ((grp ? __ldg(gst + jn) : 0u) == (u32)jn) || (__ldg(keys + jn) != vk[RR_IPT - 1]);
         hbits |= (u32)hn << RR_IPT;
     }
     if (mine < RR_IPT) hbits |= 1u << mine;  // the slot after the last live slot acts as a head
@@ -472,14 +475,26 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *__restrict__
 }
 
 // ---- emit -----------------------------------------------------------------------------------------
-// out[rank[i]] = T[i-1] for every position that does not start a factor
+// out[rank[i]] = T[i-1] for every position that does not start a factor and whose rank lies in
+// [lo, hi).  Large outputs are emitted in rank windows small enough to stay in L2, so the
+// one-byte scatter merges into full sectors there instead of read-modify-writing DRAM.
 __global__ void __launch_bounds__(256) k_emit(const u8 *__restrict__ T, u32 n, const u32 *__restrict__ rank,
-                                              const u8 *__restrict__ flags, u8 *__restrict__ out)
+                                              const u8 *__restrict__ flags, u8 *__restrict__ out, u32 lo, u32 hi)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flags[i]) return;
-    out[ldg_stream_u32(rank + i)] = T[i - 1];
+    const u32 i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    if (i0 + 4 <= n) {
+        const uint4 r = ldg_stream_u4((const uint4 *)(rank + i0));
+        const u32 rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (rr[q] >= lo && rr[q] < hi && !flags[i0 + q]) out[rr[q]] = T[i0 + q - 1];
+    } else {
+        for (u32 i = i0; i < n; i++) {
+            const u32 r = rank[i];
+            if (r >= lo && r < hi && !flags[i]) out[r] = T[i - 1];
+        }
+    }
 }
 // factor heads receive the last byte of their own factor
 __global__ void __launch_bounds__(256) k_emit_heads(const u8 *__restrict__ T, const u32 *__restrict__ FS, u32 F,

@@ -9,11 +9,15 @@
 // d(i) = prev-steps from the smallest index of i's cycle to i, off(c) = total length of
 // the cycles whose smallest index is below c's.
 //
-// d and off come from list ranking with hashed splitters: every splitter walks its
-// sublist once (k_inv_walk), the reduced list of splitters is ranked by pointer jumping
-// (min, then suffix sums cut at the sublist holding the cycle's minimum), cycles without
-// any splitter are walked directly (k_inv_self_walk), an exclusive scan over the cycle
-// lengths parked at the cycle minima gives off, and k_inv_place scatters the bytes.
+// d and off come from list ranking with hashed splitters.  Every splitter walks its sublist
+// (k_inv_walk: length, smallest index, next sublist -- it only READS prev), the reduced list
+// of splitters is ranked by pointer jumping (min, then suffix sums cut at the sublist holding
+// the cycle minimum), an exclusive scan over the cycle lengths parked at the cycle minima
+// gives off, and every splitter walks its sublist a second time (k_inv_walk_place) writing
+// its bytes at descending, consecutive output positions; the byte of element i is recovered
+// from prev[i] alone (it is the byte whose C-range holds prev[i]).  Random traffic is two
+// 4-byte reads per element and nothing else.  Cycles without any splitter (detected by the
+// sublist lengths not adding up to n) take the fallback: mark, walk themselves, place.
 #pragma once
 #include "common.cuh"
 
@@ -69,7 +73,8 @@ __global__ void __launch_bounds__(256) k_inv_colsum(const u32 *__restrict__ tile
 }
 
 // single block: per byte exclusive scan over chunks, then add C[byte]
-__global__ void __launch_bounds__(256) k_inv_chunk_scan(u32 *__restrict__ chunksum, u32 nchunks)
+__global__ void __launch_bounds__(256) k_inv_chunk_scan(u32 *__restrict__ chunksum, u32 nchunks,
+                                                        u32 *__restrict__ Cout /*[257]*/)
 {
     __shared__ u32 ws[8];
     const u32 d = threadIdx.x;
@@ -85,6 +90,8 @@ __global__ void __launch_bounds__(256) k_inv_chunk_scan(u32 *__restrict__ chunks
     u32 C = incl - run;
     for (u32 w = 0; w < (d >> 5); w++) C += ws[w];
     for (u32 c = 0; c < nchunks; c++) chunksum[c * 256 + d] += C;
+    Cout[d] = C;
+    if (d == 255) Cout[256] = C + run;
 }
 
 // tilehist -> exclusive base per (tile, byte), in place
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(256) k_inv_spl_count(u32 n, u32 shift, u32 *__
     }
 }
 __global__ void __launch_bounds__(256) k_inv_spl_write(u32 n, u32 shift, const u32 *__restrict__ tileoff,
-                                                       u32 *__restrict__ spl, uint2 *__restrict__ rec)
+                                                       u32 *__restrict__ spl, u32 *__restrict__ sid)
 {
     __shared__ u32 ws[8];
     const u32 base = blockIdx.x * SP_TILE + threadIdx.x * 16;
@@ -197,33 +204,73 @@ __global__ void __launch_bounds__(256) k_inv_spl_write(u32 n, u32 shift, const u
     for (int q = 0; q < 16; q++)
         if ((base + q < n) && is_splitter(base + q, shift)) {
             spl[s] = base + q;
-            rec[base + q] = make_uint2(s, 0u);
+            sid[base + q] = s;  // sparse: only splitter slots of sid are ever written or read
             s++;
         }
 }
 
-// one thread per splitter: follow prev until the next splitter, label the sublist.
-// rec[i] = (sublist id, offset inside the sublist); jm[s] = next sublist << 32 | smallest index
+// first walk: one thread per splitter follows prev until the next splitter.  (A persistent
+// variant with dynamic work fetch was measured slower: the limit is the dependent random
+// access rate, not warp divergence.)
+// jm[s] = next sublist << 32 | smallest index; wlen[s] = sublist length; minfo[s] = (smallest
+// index, its offset).  visited (optional) gets one bit per element reached.  *total += lengths.
 __global__ void __launch_bounds__(128) k_inv_walk(const u32 *__restrict__ prev, u32 shift,
-                                                  const u32 *__restrict__ spl, u32 ns, uint2 *__restrict__ rec,
+                                                  const u32 *__restrict__ spl, u32 ns, const u32 *__restrict__ sid,
                                                   u64 *__restrict__ jm, u32 *__restrict__ wlen,
-                                                  uint2 *__restrict__ minfo)
+                                                  uint2 *__restrict__ minfo, u32 *__restrict__ visited,
+                                                  u32 *__restrict__ total)
 {
     const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= ns) return;
-    const u32 i0 = spl[s];
-    u32 mn = i0, mo = 0, o = 1;
-    u32 i = prev[i0];
-    while (!is_splitter(i, shift)) {
-        rec[i] = make_uint2(s, o);
-        if (i < mn) { mn = i; mo = o; }
-        i = prev[i];
-        o++;
+    u32 o = 0;
+    if (s < ns) {
+        const u32 i0 = spl[s];
+        u32 mn = i0, mo = 0;
+        o = 1;
+        if (visited) atomicOr(visited + (i0 >> 5), 1u << (i0 & 31));
+        u32 i = prev[i0];
+        while (!is_splitter(i, shift)) {
+            if (visited) atomicOr(visited + (i >> 5), 1u << (i & 31));
+            if (i < mn) { mn = i; mo = o; }
+            i = prev[i];
+            o++;
+        }
+        jm[s] = ((u64)sid[i] << 32) | mn;
+        wlen[s] = o;
+        minfo[s] = make_uint2(mn, mo);
     }
-    const u32 nxt = rec[i].x;  // written by k_inv_spl_write
-    jm[s] = ((u64)nxt << 32) | mn;
-    wlen[s] = o;
-    minfo[s] = make_uint2(mn, mo);
+    if (total) {
+        o = warp_sum(o);
+        if (lane_id() == 0 && o) atomicAdd(total, o);
+    }
+}
+
+// second walk: srec[s] = (d of the splitter element, cycle length L, cycle offset off);
+// element at offset o of the sublist has d = (A + o) mod L and lands at out[n-1-off-d].
+__global__ void __launch_bounds__(128) k_inv_walk_place(const u32 *__restrict__ prev, u32 n, u32 shift,
+                                                        const u32 *__restrict__ spl, u32 ns,
+                                                        const uint4 *__restrict__ srec,
+                                                        const u32 *__restrict__ Ctab, u8 *__restrict__ out)
+{
+    __shared__ u32 sC[257];
+    for (u32 t = threadIdx.x; t < 257; t += blockDim.x) sC[t] = Ctab[t];
+    __syncthreads();
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const uint4 r = srec[s];
+    const u32 L = r.y, top = n - 1 - r.z;
+    u32 d = r.x;
+    u32 i = spl[s];
+    do {
+        const u32 p = prev[i];
+        // byte of element i: largest c with C[c] <= p
+        u32 c = 0;
+#pragma unroll
+        for (u32 step = 128; step > 0; step >>= 1)
+            if (sC[c + step] <= p) c += step;
+        out[top - d] = (u8)c;
+        if (++d == L) d = 0;
+        i = p;
+    } while (!is_splitter(i, shift));
 }
 
 // pointer jumping with min: (jmp, mn) <- (jmp[jmp], min(mn, mn[jmp]))
@@ -279,24 +326,35 @@ __global__ void __launch_bounds__(256) k_inv_origin_publish(const u64 *__restric
     }
 }
 
-// elements no walk reached belong to cycles without a splitter: walk the whole cycle.
-// rec[i] = (0x80000000 | smallest index, d(i))
-__global__ void __launch_bounds__(256) k_inv_self_walk(const u32 *__restrict__ prev, u32 n, uint2 *__restrict__ rec,
+// fallback: elements no walk reached belong to cycles without a splitter: walk the whole cycle.
+// urec[i] = (smallest index, d(i)), written (and later read) only for unreached elements.
+__global__ void __launch_bounds__(256) k_inv_self_walk(const u32 *__restrict__ prev, u32 n,
+                                                       const u32 *__restrict__ visited, uint2 *__restrict__ urec,
                                                        u32 *__restrict__ len_at_min, u32 *__restrict__ counters)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (rec[i].x != NONE32) return;
+    if ((visited[i >> 5] >> (i & 31)) & 1) return;
     u32 j = prev[i], steps = 1, mn = i, mstep = 0;
     while (j != i) {
         if (j < mn) { mn = j; mstep = steps; }
         j = prev[j];
         steps++;
     }
-    const u32 d = (mstep == 0) ? 0 : steps - mstep;
-    rec[i] = make_uint2(0x80000000u | mn, d);
-    if (mn == i) { len_at_min[i] = steps; atomicAdd(counters + 1, 1u); }
-    atomicAdd(counters + 0, 1u);
+    urec[i] = make_uint2(mn, (mstep == 0) ? 0 : steps - mstep);
+    if (mn == i) len_at_min[i] = steps;
+    atomicAdd(counters, 1u);
+}
+__global__ void __launch_bounds__(256) k_inv_place_unreached(const u8 *__restrict__ B, u32 n,
+                                                             const u32 *__restrict__ visited,
+                                                             const uint2 *__restrict__ urec,
+                                                             const u32 *__restrict__ off, u8 *__restrict__ out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((visited[i >> 5] >> (i & 31)) & 1) return;
+    const uint2 r = urec[i];
+    out[n - 1 - off[r.x] - r.y] = B[i];
 }
 
 // per sublist: (A, L, off) with d(i) = (A + offset(i)) mod L
@@ -312,25 +370,6 @@ __global__ void __launch_bounds__(256) k_inv_spl_record(const u64 *__restrict__ 
     u32 A = (L - (u32)pvR[s]) + (L - c.y);  // P(s) + L - o(m), both terms in (0, L]
     while (A >= L) A -= L;
     srec[s] = make_uint4(A, L, off[cm], 0u);
-}
-
-__global__ void __launch_bounds__(256) k_inv_place(const u8 *__restrict__ B, u32 n, const uint2 *__restrict__ rec,
-                                                   const uint4 *__restrict__ srec, const u32 *__restrict__ off,
-                                                   u8 *__restrict__ out)
-{
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint2 r = rec[i];
-    u32 pos;
-    if (r.x & 0x80000000u) {
-        pos = n - 1 - __ldg(off + (r.x & 0x7fffffffu)) - r.y;
-    } else {
-        const uint4 q = __ldg(srec + r.x);
-        u32 d = q.x + r.y;
-        if (d >= q.y) d -= q.y;
-        pos = n - 1 - q.z - d;
-    }
-    out[pos] = B[i];
 }
 
 // count cycles: entries of len_at_min that are non-zero
