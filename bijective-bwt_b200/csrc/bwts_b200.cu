@@ -488,9 +488,12 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     uint4 *srec = arena_take<uint4>(ctx, ns);
     if (!spl || !jm[0] || !jm[1] || !jm[2] || !pv[0] || !pv[1] || !wlen || !minfo || !srec) return BWTS_B200_EINTERNAL;
     LAUNCH(KC_INV_WALK, 8.0 * ns, k_inv_spl_write, nst, 256, n, shift, tilecnt, spl, sid);
-    // first walk: 4 B read per element
+    // first walk: 4 B read per element, one visited bit set per element (bitmap lives in L2)
+    u32 *visited = arena_take<u32>(ctx, (size_t)(n >> 5) + 2);
+    if (!visited) return BWTS_B200_EINTERNAL;
+    CK(cudaMemsetAsync(visited, 0, ((size_t)(n >> 5) + 2) * 4, st));
     LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
-           (u32 *)nullptr, small + 2);
+           visited, small + 2);
 
     // -- reduced list: cycle minimum, then distance to the sublist holding it
     const int R = bit_length((u64)ns - 1) + 1;
@@ -514,16 +517,12 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     rc = readback(ctx, st, small + 2, 4);
     if (rc) return rc;
     const u32 reached = ctx->h_small[0];
-    u32 *visited = nullptr;
     uint2 *urec = nullptr;
+    const u32 nwords = cdiv(n, 32);
     if (reached != n) {
-        visited = arena_take<u32>(ctx, (size_t)(n >> 5) + 2);
         urec = arena_take<uint2>(ctx, n);
-        if (!visited || !urec) return BWTS_B200_EINTERNAL;
-        CK(cudaMemsetAsync(visited, 0, ((size_t)(n >> 5) + 2) * 4, st));
-        LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
-               visited, (u32 *)nullptr);
-        LAUNCH(KC_INV_WALK, 12.0 * (n - reached), k_inv_self_walk, cdiv(n, 256), 256, prev, n, visited, urec,
+        if (!urec) return BWTS_B200_EINTERNAL;
+        LAUNCH(KC_INV_WALK, 12.0 * (n - reached), k_inv_self_walk, cdiv(nwords, 256), 256, prev, n, visited, urec,
                len_at_min, small + 4);
     }
 
@@ -536,9 +535,9 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     // -- placement: second walk writes the bytes at descending consecutive positions
     LAUNCH(KC_INV_PLACE, 44.0 * ns, k_inv_spl_record, gs, 256, jmR, pv[pc], cyc, off, ns, srec);
     LAUNCH(KC_INV_PLACE, 5.0 * n, k_inv_walk_place, cdiv(ns, 128), 128, prev, n, shift, spl, ns, srec, Ctab, d_out);
-    if (visited)
-        LAUNCH(KC_INV_PLACE, 14.0 * (n - reached), k_inv_place_unreached, cdiv(n, 256), 256, dB, n, visited, urec, off,
-               d_out);
+    if (urec)
+        LAUNCH(KC_INV_PLACE, 14.0 * (n - reached), k_inv_place_unreached, cdiv(nwords, 256), 256, dB, n, visited, urec,
+               off, d_out);
 
     rc = readback(ctx, st, small, 40);
     if (rc) return rc;

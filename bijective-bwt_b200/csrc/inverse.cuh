@@ -17,7 +17,8 @@
 // its bytes at descending, consecutive output positions; the byte of element i is recovered
 // from prev[i] alone (it is the byte whose C-range holds prev[i]).  Random traffic is two
 // 4-byte reads per element and nothing else.  Cycles without any splitter (detected by the
-// sublist lengths not adding up to n) take the fallback: mark, walk themselves, place.
+// sublist lengths not adding up to n; the first walk also sets a visited bit per element, the
+// bitmap stays in L2) take the fallback: walk themselves, place.
 #pragma once
 #include "common.cuh"
 
@@ -327,34 +328,45 @@ __global__ void __launch_bounds__(256) k_inv_origin_publish(const u64 *__restric
 }
 
 // fallback: elements no walk reached belong to cycles without a splitter: walk the whole cycle.
-// urec[i] = (smallest index, d(i)), written (and later read) only for unreached elements.
+// One thread per word of the visited bitmap.  urec[i] = (smallest index, d(i)), written (and
+// later read) only for unreached elements.
 __global__ void __launch_bounds__(256) k_inv_self_walk(const u32 *__restrict__ prev, u32 n,
                                                        const u32 *__restrict__ visited, uint2 *__restrict__ urec,
                                                        u32 *__restrict__ len_at_min, u32 *__restrict__ counters)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if ((visited[i >> 5] >> (i & 31)) & 1) return;
-    u32 j = prev[i], steps = 1, mn = i, mstep = 0;
-    while (j != i) {
-        if (j < mn) { mn = j; mstep = steps; }
-        j = prev[j];
-        steps++;
+    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((u64)w * 32 >= n) return;
+    u32 todo = ~visited[w];
+    if ((u64)w * 32 + 32 > n) todo &= (1u << (n - w * 32)) - 1;
+    while (todo) {
+        const u32 i = w * 32 + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        u32 j = prev[i], steps = 1, mn = i, mstep = 0;
+        while (j != i) {
+            if (j < mn) { mn = j; mstep = steps; }
+            j = prev[j];
+            steps++;
+        }
+        urec[i] = make_uint2(mn, (mstep == 0) ? 0 : steps - mstep);
+        if (mn == i) len_at_min[i] = steps;
+        atomicAdd(counters, 1u);
     }
-    urec[i] = make_uint2(mn, (mstep == 0) ? 0 : steps - mstep);
-    if (mn == i) len_at_min[i] = steps;
-    atomicAdd(counters, 1u);
 }
 __global__ void __launch_bounds__(256) k_inv_place_unreached(const u8 *__restrict__ B, u32 n,
                                                              const u32 *__restrict__ visited,
                                                              const uint2 *__restrict__ urec,
                                                              const u32 *__restrict__ off, u8 *__restrict__ out)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if ((visited[i >> 5] >> (i & 31)) & 1) return;
-    const uint2 r = urec[i];
-    out[n - 1 - off[r.x] - r.y] = B[i];
+    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((u64)w * 32 >= n) return;
+    u32 todo = ~visited[w];
+    if ((u64)w * 32 + 32 > n) todo &= (1u << (n - w * 32)) - 1;
+    while (todo) {
+        const u32 i = w * 32 + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const uint2 r = urec[i];
+        out[n - 1 - off[r.x] - r.y] = B[i];
+    }
 }
 
 // per sublist: (A, L, off) with d(i) = (A + offset(i)) mod L
