@@ -45,7 +45,7 @@ class Stats(ctypes.Structure):
         ("total_ms", ctypes.c_double),
         ("class_launches", ctypes.c_long * NCLASS), ("class_ms", ctypes.c_double * NCLASS),
         ("class_bytes", ctypes.c_double * NCLASS),
-        ("h2d_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
+        ("h2d_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double), ("lyndon_fallback", ctypes.c_int),
     ]
 
 

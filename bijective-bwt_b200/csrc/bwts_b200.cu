@@ -39,6 +39,7 @@ static long g_tune_chunk = 0;      // Lyndon chunk bytes (0 = auto)
 static long g_tune_spl_shift = 0;  // splitter shift   (0 = 26)
 static long g_tune_onesweep = 0;   // onesweep tile configuration (see radix_sort)
 static long g_tune_local = 0;      // 1 = never use the warp-local sort path
+static long g_tune_lyndon = 0;     // 1 = always take the suffix-sort fallback for the Lyndon boundaries
 
 struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; };
 
@@ -205,9 +206,15 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
 }
 
 // ---- forward ---------------------------------------------------------------------------------
-// linear != 0: suffix-array mode (successor i+1, end of text smallest) -- fills d_sa instead of d_out.
-static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 *d_sa, int linear, cudaStream_t st)
+enum FwdMode {
+    FWD_BWTS = 0,        // forward BWTS into d_out
+    FWD_SA = 1,          // suffix array into d_sa (successor i+1, end of text smallest)
+    FWD_LYNDON = 2,      // suffix sort, then factor-start flags (prefix minima of the ISA) into d_out
+    FWD_BWTS_FLAGS = 3   // forward BWTS, factor-start flags already in d_out (after FWD_LYNDON)
+};
+static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 *d_sa, int mode, cudaStream_t st)
 {
+    const int linear = (mode == FWD_SA || mode == FWD_LYNDON);
     int rc = arena_reserve(ctx, workspace_bytes(n));
     if (rc) return rc;
     ctx->arena_used = 0;
@@ -253,7 +260,9 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     CK(cudaMemsetAsync(sb.status, 0, (size_t)os_tiles * RADIX_BINS * sizeof(u64), st));
     u32 F = 1, lmax = n;
 
-    if (!linear) {
+    if (mode == FWD_BWTS_FLAGS) {
+        CK(cudaMemcpyAsync(flags, d_out, n, cudaMemcpyDeviceToDevice, st));
+    } else if (!linear) {
         // -- Lyndon boundaries
         u32 chunk = g_tune_chunk > 0 ? (u32)g_tune_chunk : max(512u, cdiv(n, 1u << 21));
         const u32 nch = cdiv(n, chunk), ngroups = cdiv(nch, LY_GROUP);
@@ -262,19 +271,28 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         u32 *group_alt = arena_take<u32>(ctx, ngroups);
         if (!chunk_last || !group_min || !group_alt) return BWTS_B200_EINTERNAL;
         CK(cudaMemsetAsync(flags, 0, n, st));
-        LAUNCH(KC_LYNDON, 2.0 * n, k_duval_chunks, cdiv(nch, 128), 128, dT, n, chunk, nch, flags, chunk_last);
+        // work budgets: all Duval threads together may run n bytes (at least 32 MiB) past their
+        // chunks, a warp may compare 16 MiB; beyond that the text is periodic enough for the
+        // suffix-sort route to be cheaper
+        LyBudget bud_thread = {small + 3, g_tune_lyndon ? 0u : max(1u << 22, n >> 3), small + 4};
+        LyBudget bud_warp = {small + 3, g_tune_lyndon ? 0u : (16u << 10), small + 4};
+        if (g_tune_lyndon) CK(cudaMemsetAsync(small + 3, 0xff, 4, st));
+        LAUNCH(KC_LYNDON, 2.0 * n, k_duval_chunks, cdiv(nch, 128), 128, dT, n, chunk, nch, flags, chunk_last,
+               bud_thread);
         if (nch > 1) {
             LAUNCH(KC_LYNDON, 0, k_chunkmin_reduce, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk_last, nch,
-                   group_min, ngroups);
+                   group_min, ngroups, bud_warp);
             u32 *gin = group_min, *gout = group_alt;
             for (u32 stride = 1; stride < ngroups; stride <<= 1) {
                 LAUNCH(KC_LYNDON, 0, k_chunkmin_level, cdiv((u64)ngroups * 32, 128), 128, dT, n, gin, gout, ngroups,
-                       stride);
+                       stride, bud_warp);
                 u32 *t = gin; gin = gout; gout = t;
             }
             LAUNCH(KC_LYNDON, 0, k_chunk_threshold, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk, nch, flags,
-                   chunk_last, gin, ngroups);
+                   chunk_last, gin, ngroups, bud_warp);
         }
+    }
+    if (!linear) {
         // -- factor table
         LAUNCH(KC_FACTORS, 1.0 * n, k_flag_count, ntl, 256, flags, n, tilecnt);
         LAUNCH(KC_FACTORS, 8.0 * ntl, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, ntl, small + 0);
@@ -287,6 +305,14 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     rc = readback(ctx, st, small, 16);
     if (rc) return rc;
     const u32 sigma = ctx->h_small[2];
+    if (mode == FWD_BWTS && ctx->h_small[3]) {
+        // the chunk kernels ran over budget, their marks are unusable: take the factor starts
+        // from a suffix sort (prefix minima of the ISA) and start again with them
+        ctx->stats.lyndon_fallback = 1;
+        rc = forward_core(ctx, dT, n, d_out, nullptr, FWD_LYNDON, st);
+        if (rc) return rc;
+        return forward_core(ctx, dT, n, d_out, nullptr, FWD_BWTS_FLAGS, st);
+    }
     if (!linear) {
         F = ctx->h_small[0];
         if (F < 1 || F > n) return BWTS_B200_EINTERNAL;
@@ -431,8 +457,14 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                    (u32)lo, hi);
         }
         LAUNCH(KC_EMIT, 10.0 * F, k_emit_heads, cdiv(F, 256), 256, dT, FS, F, rank, d_out);
-    } else {
+    } else if (mode == FWD_SA) {
         LAUNCH(KC_EMIT, 8.0 * n, k_emit_sa, cdiv(n, 256), 256, rank, n, d_sa);
+    } else {
+        // FWD_LYNDON: rank[] is now the inverse suffix array; factor starts = its strict prefix minima
+        const u32 pmt = cdiv(n, PM_TILE);
+        LAUNCH(KC_LYNDON, 4.0 * n, k_tile_min_u32, pmt, 256, rank, n, tilecnt);
+        LAUNCH(KC_LYNDON, 8.0 * pmt, k_tile_min_scan, 1, 1024, tilecnt, pmt);
+        LAUNCH(KC_LYNDON, 5.0 * n, k_prefix_min_flags, pmt, 256, rank, n, tilecnt, d_out);
     }
     ctx->stats.factors = F;
     ctx->stats.longest_factor = lmax;
@@ -622,7 +654,7 @@ static int run_device(bwts_b200_ctx *ctx, int direction, const void *d_in, long 
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->own_stream;
     stats_begin(ctx, len, direction, st);
-    rc = direction == 0 ? forward_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, nullptr, 0, st)
+    rc = direction == 0 ? forward_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, nullptr, FWD_BWTS, st)
                         : inverse_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, st);
     if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
     stats_end(ctx, st);
@@ -657,7 +689,7 @@ static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, 
     CK(cudaMemcpyAsync(d_in, in, (size_t)len, cudaMemcpyHostToDevice, st));
     ctx->io_in = d_in;  // tells the cores to skip the I/O region of the arena
     stats_begin(ctx, len, direction, st);
-    rc = direction == 0 ? forward_core(ctx, d_in, (u32)len, d_out, nullptr, 0, st)
+    rc = direction == 0 ? forward_core(ctx, d_in, (u32)len, d_out, nullptr, FWD_BWTS, st)
                         : inverse_core(ctx, d_in, (u32)len, d_out, st);
     ctx->io_in = nullptr;
     if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
@@ -782,7 +814,7 @@ extern "C" int bwts_b200_divsufsort(const unsigned char *T, int *SA, int n, int 
     CK(cudaMemcpyAsync(d_in, T, (size_t)n, cudaMemcpyHostToDevice, st));
     ctx->io_in = d_in;
     stats_begin(ctx, n, 0, st);
-    rc = forward_core(ctx, d_in, (u32)n, nullptr, d_sa, 1, st);
+    rc = forward_core(ctx, d_in, (u32)n, nullptr, d_sa, FWD_SA, st);
     ctx->io_in = nullptr;
     if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
     stats_end(ctx, st);
@@ -828,6 +860,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 0) { if (value < 0) return BWTS_B200_EINVAL; g_tune_chunk = value; return 0; }
     if (key == 1) { if (value != 0 && (value < 20 || value > 31)) return BWTS_B200_EINVAL; g_tune_spl_shift = value; return 0; }
     if (key == 3) { g_tune_local = value; return 0; }
+    if (key == 4) { g_tune_lyndon = value; return 0; }
     if (key == 2) { if (value < 0 || value > 3) return BWTS_B200_EINVAL; g_tune_onesweep = value; return 0; }
     return BWTS_B200_EINVAL;
 }

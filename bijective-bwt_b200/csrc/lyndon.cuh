@@ -16,8 +16,21 @@
 
 #define LY_GROUP 32  // chunks per warp in the min-scan kernels
 
+// Work budget of the chunk kernels.  Periodic texts (a^n, a long run of zeros, ...) make
+// the comparisons below run to the end of the periodic stretch for every chunk, which is
+// quadratic; when a thread / warp has spent more than its budget it raises *abort and every
+// kernel winds down quickly.  The host then takes the factor starts from a suffix sort
+// instead (strict prefix minima of the inverse suffix array, the reference's own criterion).
+struct LyBudget {
+    u32 *abort;      // global flag
+    u32 limit;       // per warp: KiB of comparison; Duval: 8-byte steps past the chunk, all threads together
+    u32 *counter;    // Duval only: global count of such steps
+};
+
 // T[a..n) < T[b..n) for a != b; whole warp cooperates (uniform arguments and result).
-static __device__ __forceinline__ bool suffix_less_warp(const u8 *__restrict__ T, u32 n, u32 a, u32 b)
+// `spent` accumulates KiB compared by this warp; gives up (result meaningless) once over budget.
+static __device__ __forceinline__ bool suffix_less_warp(const u8 *__restrict__ T, u32 n, u32 a, u32 b,
+                                                        const LyBudget &bud, u32 &spent)
 {
     const u32 lane = lane_id();
     u32 off = 0;
@@ -35,7 +48,19 @@ static __device__ __forceinline__ bool suffix_less_warp(const u8 *__restrict__ T
             first = 0;  // too close to the end: let the byte loop decide
         }
         const u32 mask = __ballot_sync(FULL_MASK, first < 4);
-        if (mask == 0) { off += 1024; continue; }
+        if (mask == 0) {
+            off += 1024;
+            spent++;
+            if ((spent & 63) == 0) {
+                u32 stop = 0;
+                if (lane == 0) {
+                    if (spent > bud.limit) atomicExch(bud.abort, 1u);
+                    stop = *(volatile u32 *)bud.abort;
+                }
+                if (__shfl_sync(FULL_MASK, stop, 0)) return false;
+            }
+            continue;
+        }
         const u32 l = __ffs(mask) - 1;
         const u32 w = __shfl_sync(FULL_MASK, first, l);
         u32 p = a + off + l * 32 + w * 8, q = b + off + l * 32 + w * 8;
@@ -50,10 +75,12 @@ static __device__ __forceinline__ bool suffix_less_warp(const u8 *__restrict__ T
 
 // ---- 1. Duval per chunk -----------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_duval_chunks(const u8 *__restrict__ T, u32 n, u32 chunk, u32 nch,
-                                                      u8 *__restrict__ flags, u32 *__restrict__ chunk_last)
+                                                      u8 *__restrict__ flags, u32 *__restrict__ chunk_last,
+                                                      LyBudget bud)
 {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nch) return;
+    u32 spent = 0;  // 8-byte steps taken past the end of the chunk
     const u32 b = t * chunk;
     const u32 e = min(n, b + chunk);
     u32 f = b, last = b;
@@ -69,7 +96,13 @@ __global__ void __launch_bounds__(128) k_duval_chunks(const u8 *__restrict__ T, 
             if (ci < ck) { i = f; k++; continue; }
             i++; k++;
             // inside a periodic stretch: skip 8 bytes at a time (i < k)
-            while ((u64)k + 16 <= n && load8_unaligned(T + i) == load8_unaligned(T + k)) { i += 8; k += 8; }
+            while ((u64)k + 16 <= n && load8_unaligned(T + i) == load8_unaligned(T + k)) {
+                i += 8; k += 8;
+                if (k >= e && ((++spent) & 1023) == 0) {
+                    if (atomicAdd(bud.counter, 1024u) > bud.limit) atomicExch(bud.abort, 1u);
+                    if (*(volatile u32 *)bud.abort) { chunk_last[t] = last; return; }
+                }
+            }
         }
         if (settled) {  // T[f..] is one pending word reaching beyond the chunk: f is its only start
             flags[f] = 1;
@@ -88,35 +121,36 @@ __global__ void __launch_bounds__(128) k_duval_chunks(const u8 *__restrict__ T, 
 }
 
 // ---- 2. exclusive prefix minimum of chunk_last in suffix order ---------------------------
-static __device__ __forceinline__ u32 suffix_min_warp(const u8 *T, u32 n, u32 a, u32 b)
+static __device__ __forceinline__ u32 suffix_min_warp(const u8 *T, u32 n, u32 a, u32 b, const LyBudget &bud,
+                                                      u32 &spent)
 {
     if (a == NONE32) return b;
     if (b == NONE32) return a;
-    return suffix_less_warp(T, n, b, a) ? b : a;
+    return suffix_less_warp(T, n, b, a, bud, spent) ? b : a;
 }
 
 // one warp per group of LY_GROUP chunks
 __global__ void __launch_bounds__(128) k_chunkmin_reduce(const u8 *__restrict__ T, u32 n,
                                                          const u32 *__restrict__ chunk_last, u32 nch,
-                                                         u32 *__restrict__ group_min, u32 ngroups)
+                                                         u32 *__restrict__ group_min, u32 ngroups, LyBudget bud)
 {
     const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= ngroups) return;
     const u32 lo = g * LY_GROUP, hi = min(nch, lo + LY_GROUP);
-    u32 run = NONE32;
-    for (u32 t = lo; t < hi; t++) run = suffix_min_warp(T, n, run, chunk_last[t]);
+    u32 run = NONE32, spent = 0;
+    for (u32 t = lo; t < hi; t++) run = suffix_min_warp(T, n, run, chunk_last[t], bud, spent);
     if (lane_id() == 0) group_min[g] = run;
 }
 
 // one Hillis-Steele level of the inclusive prefix minimum over the groups (warp per group):
 // out[g] = min(in[g], in[g - stride]).  ceil(log2(ngroups)) launches, ping-pong buffers.
 __global__ void __launch_bounds__(128) k_chunkmin_level(const u8 *__restrict__ T, u32 n, const u32 *__restrict__ in,
-                                                        u32 *__restrict__ out, u32 ngroups, u32 stride)
+                                                        u32 *__restrict__ out, u32 ngroups, u32 stride, LyBudget bud)
 {
     const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= ngroups) return;
-    u32 v = in[g];
-    if (g >= stride) v = suffix_min_warp(T, n, in[g - stride], v);
+    u32 v = in[g], spent = 0;
+    if (g >= stride) v = suffix_min_warp(T, n, in[g - stride], v, bud, spent);
     if (lane_id() == 0) out[g] = v;
 }
 
@@ -147,19 +181,26 @@ static __device__ void clear_flags_warp(u8 *flags, u32 lo, u32 hi)
 
 __global__ void __launch_bounds__(128) k_chunk_threshold(const u8 *__restrict__ T, u32 n, u32 chunk, u32 nch,
                                                          u8 *__restrict__ flags, const u32 *__restrict__ chunk_last,
-                                                         const u32 *__restrict__ group_incl, u32 ngroups)
+                                                         const u32 *__restrict__ group_incl, u32 ngroups,
+                                                         LyBudget bud)
 {
     const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= ngroups) return;
     const u32 lo = g * LY_GROUP, hi = min(nch, lo + LY_GROUP);
     u32 run = g ? group_incl[g - 1] : NONE32;
+    u32 spent = 0;
     for (u32 t = lo; t < hi; t++) {
         const u32 mlast = chunk_last[t];
         if (run != NONE32) {
             const u32 b = t * chunk, e = min(n, b + chunk);
-            if (!suffix_less_warp(T, n, mlast, run)) {
+            {
+                u32 stop = 0;
+                if (lane_id() == 0) stop = *(volatile u32 *)bud.abort;
+                if (__shfl_sync(FULL_MASK, stop, 0)) return;  // warp-uniform exit
+            }
+            if (!suffix_less_warp(T, n, mlast, run, bud, spent)) {
                 clear_flags_warp(flags, b, e);  // nothing in this chunk beats the earlier minimum
-            } else if (!suffix_less_warp(T, n, b, run)) {
+            } else if (!suffix_less_warp(T, n, b, run, bud, spent)) {
                 // marks are decreasing in suffix order: first (=b) fails, last succeeds
                 u32 c = 0;
                 {
@@ -173,13 +214,86 @@ __global__ void __launch_bounds__(128) k_chunk_threshold(const u8 *__restrict__ 
                 while (z - a > 1) {
                     const u32 mid = (a + z) >> 1;
                     const u32 pos = select_mark_warp(flags, b, e, mid);
-                    if (suffix_less_warp(T, n, pos, run)) { z = mid; zpos = pos; } else a = mid;
+                    if (suffix_less_warp(T, n, pos, run, bud, spent)) { z = mid; zpos = pos; } else a = mid;
                 }
                 clear_flags_warp(flags, b, zpos);
             }
             __syncwarp();
         }
-        run = suffix_min_warp(T, n, run, mlast);
+        run = suffix_min_warp(T, n, run, mlast, bud, spent);
+    }
+}
+
+// ---- fallback: factor starts = strict prefix minima of the inverse suffix array ---------------
+// (the reference's criterion, /root/reference/mk_bwts_sa.c:126-129).  isa = ranks of a suffix sort.
+#define PM_TILE 4096
+__global__ void __launch_bounds__(256) k_tile_min_u32(const u32 *__restrict__ isa, u32 n, u32 *__restrict__ tile_min)
+{
+    __shared__ u32 ws[8];
+    const u32 base = blockIdx.x * PM_TILE;
+    u32 v = NONE32;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const u32 i = base + q * 256 + threadIdx.x;
+        if (i < n) v = min(v, isa[i]);
+    }
+    v = warp_min(v);
+    if (lane_id() == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = NONE32;
+        for (int w = 0; w < 8; w++) t = min(t, ws[w]);
+        tile_min[blockIdx.x] = t;
+    }
+}
+// single block: exclusive prefix minimum of the tile minima, in place
+__global__ void __launch_bounds__(1024) k_tile_min_scan(u32 *__restrict__ tile_min, u32 ntiles)
+{
+    __shared__ u32 part[1024];
+    const u32 per = (ntiles + 1023) / 1024;
+    const u32 lo = min(ntiles, threadIdx.x * per), hi = min(ntiles, lo + per);
+    u32 v = NONE32;
+    for (u32 t = lo; t < hi; t++) v = min(v, tile_min[t]);
+    part[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 run = NONE32;
+        for (u32 t = 0; t < 1024; t++) { const u32 x = part[t]; part[t] = run; run = min(run, x); }
+    }
+    __syncthreads();
+    u32 run = part[threadIdx.x];
+    for (u32 t = lo; t < hi; t++) { const u32 x = tile_min[t]; tile_min[t] = run; run = min(run, x); }
+}
+// flags[i] = isa[i] < min(isa[0..i))   (thread owns 16 consecutive positions)
+__global__ void __launch_bounds__(256) k_prefix_min_flags(const u32 *__restrict__ isa, u32 n,
+                                                          const u32 *__restrict__ tile_excl, u8 *__restrict__ flags)
+{
+    __shared__ u32 ws[8];
+    const u32 base = blockIdx.x * PM_TILE + threadIdx.x * 16;
+    u32 v[16];
+    u32 mine = NONE32;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        v[q] = (base + q < n) ? isa[base + q] : NONE32;
+        mine = min(mine, v[q]);
+    }
+    // exclusive prefix minimum over the threads of the block
+    u32 incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane_id() >= (u32)o) incl = min(incl, y);
+    }
+    if (lane_id() == 31) ws[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 run = __shfl_up_sync(FULL_MASK, incl, 1);
+    if (lane_id() == 0) run = NONE32;
+    run = min(run, tile_excl[blockIdx.x]);
+    for (u32 w = 0; w < (threadIdx.x >> 5); w++) run = min(run, ws[w]);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        if (base + q < n) flags[base + q] = (v[q] < run) ? 1 : 0;  // position 0: run == NONE32
+        run = min(run, v[q]);
     }
 }
 

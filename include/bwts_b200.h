@@ -110,6 +110,7 @@ typedef struct {
     /* host-buffer entry points only: CUDA-event times of the two copies around the transform */
     double h2d_ms;
     double d2h_ms;
+    int    lyndon_fallback;     /* forward: 1 if the Lyndon boundaries came from the suffix-sort fallback */
 } bwts_b200_stats;
 
 int bwts_b200_get_stats(const bwts_b200_ctx *ctx, bwts_b200_stats *out);
@@ -123,7 +124,8 @@ const char *bwts_b200_version(void);
 /* Test hooks: override tuning constants so that small inputs exercise the multi-tile /
  * multi-chunk paths.  key: 0 = Lyndon chunk bytes (>= 1), 1 = inverse splitter shift
  * (density 2^-(32-shift), 20..31), 2 = onesweep tile shape (0..3), 3 = disable the
- * warp-local sort path (1).  value 0 = default.       */
+ * warp-local sort path (1), 4 = force the suffix-sort fallback for the Lyndon boundaries (1).
+ * value 0 = default.       */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

@@ -236,3 +236,34 @@ def test_local_sort_path_and_radix_only_path_agree(bwts, ctx, oracle, gen):
         b = ctx.forward_host(x)
         assert a == want and b == want
         assert ra == 0
+
+
+def test_lyndon_suffix_sort_fallback(bwts, ctx, oracle, gen):
+    """factor starts taken from the strict prefix minima of a GPU-built inverse suffix array
+    (the reference's own criterion, mk_bwts_sa.c:126-129) -- the route periodic inputs take
+    when the chunk kernels run out of budget -- forced here on every kind of input"""
+    bwts.tune(4, 1)
+    try:
+        for v in GOLDEN:
+            if v["n"] > 70_000 or "input" not in v:
+                continue
+            x = bytes.fromhex(v["input"])
+            assert ctx.forward_host(x) == bytes.fromhex(v["fwd"]), v["name"]
+            assert ctx.stats()["lyndon_fallback"] == 1
+        for kind, seed, n in (("text", 3, 300_000), ("dna", 4, 200_000), ("tiled", 5, 500_000)):
+            x = gen.make(kind, seed, n)
+            assert ctx.forward_host(x) == oracle.forward(x), kind
+        for name, x in helpers.families(65_537).items():
+            assert ctx.forward_host(x) == oracle.forward(x), name
+    finally:
+        bwts.tune(4, 0)
+
+
+def test_periodic_inputs_trigger_the_fallback_by_budget(bwts, ctx, oracle):
+    """a^n and a short-period text at 8 MiB exhaust the chunk kernels' budget on their own"""
+    n = 8 << 20
+    for x in (b"a" * n, (b"abcabd" * (n // 6 + 1))[:n]):
+        y = ctx.forward_host(x)
+        assert ctx.stats()["lyndon_fallback"] == 1
+        assert y == oracle.forward(x)
+        assert ctx.inverse_host(y) == x
