@@ -194,7 +194,7 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
     } while (0)
         switch (g_tune_onesweep) {
         case 1: OS_LAUNCH(512, 8, 2, 16); break;
-        case 2: OS_LAUNCH(512, 8, 2, 4); break;
+        case 2: OS_LAUNCH(1024, 8, 1, 8); break;
         case 3: OS_LAUNCH(256, 8, 4, 8); break;
         default: OS_LAUNCH(512, 8, 2, 8); break;
         }
@@ -598,7 +598,7 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
                          (int)OsSmem<NT_, IPT_>::bytes);                                                         \
     cudaFuncSetAttribute(k_onesweep_pass<NT_, IPT_, MINB_, LB_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
     OS_ATTR(512, 8, 2, 8);
-    OS_ATTR(512, 8, 2, 4);
+    OS_ATTR(1024, 8, 1, 8);
     OS_ATTR(256, 8, 4, 8);
     OS_ATTR(512, 8, 2, 16);
 #undef OS_ATTR

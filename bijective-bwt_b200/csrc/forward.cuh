@@ -515,8 +515,3 @@ __global__ void k_set_u32(u32 *p, const u32 *idx_src, u32 value)
 {
     p[*idx_src] = value;  // FS[F] = n
 }
-__global__ void __launch_bounds__(256) k_iota_u32(u32 *p, u32 n)
-{
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = i;
-}
