@@ -59,6 +59,26 @@ def total_blocks(workload, world):
 DOMINANT = "onesweep_pass"
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep the real stdout for the one JSON line; whatever libraries print to fd 1 (NCCL's
+    version banner, for one) goes to stderr instead."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit_json(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_product():
     import importlib.util
     spec = importlib.util.spec_from_file_location("bwts_b200", REPO / "bijective-bwt_b200" / "bwts_b200.py")
@@ -211,7 +231,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -410,7 +430,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                           + ("unmodified reference mk_bwts + unbwts from oracle/_ref (suffix sort = substitute SA-IS, "
                              "not libdivsufsort), 1 thread" if kind == "reference" else "oracle port, 1 thread"),
                 "host_cpus": os.cpu_count()}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     ctx.close()
     if dist:
         dist.destroy_process_group()
@@ -432,6 +452,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        claim_stdout()
         run_reference_arm(args, rank, world)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
@@ -439,6 +460,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", str(Path(__file__).resolve())] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    claim_stdout()
     run_gpu_arm(args, rank, local_rank, world)
 
 

@@ -48,7 +48,7 @@ struct bwts_b200_ctx {
     cudaStream_t own_stream = nullptr;
     u8 *arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
-    u8 *io_in = nullptr, *io_out = nullptr;  // device staging of the host-buffer API
+    u8 *io_in = nullptr;     // host-buffer API: start of the I/O region at the bottom of the arena (while a call runs)
     size_t io_bytes = 0;
     u32 *h_small = nullptr;  // pinned, 4 KiB, for counter read-backs
     int last_cuda = 0;
@@ -626,7 +626,6 @@ extern "C" void bwts_b200_destroy(bwts_b200_ctx *ctx)
     if (ctx->ev_io0) cudaEventDestroy(ctx->ev_io0);
     if (ctx->ev_io1) cudaEventDestroy(ctx->ev_io1);
     if (ctx->arena) cudaFree(ctx->arena);
-    if (ctx->io_in) cudaFree(ctx->io_in);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     delete ctx;
 }
