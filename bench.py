@@ -104,13 +104,14 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from before the warm-up on;
+    stop() keeps the samples whose timestamps fall inside the timed regions."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0 = index, [], None, None
 
     def start(self):
         try:
@@ -124,30 +125,45 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """the timed region starts now"""
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t1 = time.time()
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+
+        def digest(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                except Exception:
+                    continue
+                for name, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            sm.sort()
+            return sm, mx, reasons
+
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 - 0.05 <= x[0] <= t1 + 0.1]
+        sm, mx, reasons = digest(inside)
+        window = "timed regions"
+        if not sm:  # region shorter than the sampling period: report what was seen around it
+            sm, mx, reasons = digest(self.rows)
+            window = "whole run (timed region shorter than the sampling period)"
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------- CPU arms
@@ -307,6 +323,8 @@ def run_gpu_arm(args, rank, local_rank, world):
         for b in blocks:
             assert torch.equal(b["d_back"], b["d_in"]), "round trip lost data"
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---- warm-up (also the correctness gate of the bench itself)
     for _ in range(args.warmup):
         device_step()
@@ -315,9 +333,8 @@ def run_gpu_arm(args, rank, local_rank, world):
         check_round_trip()
 
     # ---- timed region: exactly K steps, device resident
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     t_begin = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_begin.record(stream)
     evs = []
