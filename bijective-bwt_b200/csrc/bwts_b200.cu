@@ -165,14 +165,24 @@ struct SortBufs {
     u64 *status;    // tiles * 256
 };
 
-static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, int passes, bool identity_vals)
+static int radix_prepare(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb)
 {
-    if (passes < 1) passes = 1;
-    if (passes > RADIX_MAX_PASSES) return BWTS_B200_EINTERNAL;
     CK(cudaMemsetAsync(sb.hist, 0, (RADIX_MAX_PASSES * RADIX_BINS + RADIX_MAX_PASSES) * sizeof(u32), st));
+    return 0;
+}
+
+// have_hist: the digit histograms are already in sb.hist (radix_prepare + the key-building kernel)
+static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, int passes, bool identity_vals,
+                      bool have_hist)
+{
+    if (passes < 1 || passes > RADIX_MAX_PASSES) return BWTS_B200_EINTERNAL;
     u32 *tickets = sb.hist + RADIX_MAX_PASSES * RADIX_BINS;
-    const u32 hgrid = min(cdiv(m, 256), 148u * 8u);
-    LAUNCH(KC_RADIX_HIST, 8.0 * m, k_radix_hist, hgrid, 256, sb.k[sb.cur], m, passes, sb.hist);
+    if (!have_hist) {
+        int rc0 = radix_prepare(ctx, st, sb);
+        if (rc0) return rc0;
+        const u32 hgrid = min(cdiv(m, 256), 148u * 8u);
+        LAUNCH(KC_RADIX_HIST, 8.0 * m, k_radix_hist, hgrid, 256, sb.k[sb.cur], m, passes, sb.hist);
+    }
     LAUNCH(KC_RADIX_HIST, 0, k_radix_hist_scan, passes, 256, sb.hist);
     for (int p = 0; p < passes; p++) {
         const int a = sb.cur, b = sb.cur ^ 1;
@@ -332,7 +342,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     } else {
         LAUNCH(KC_INIT_KEYS, 9.0 * n, k_init_keys_linear, cdiv(cdiv(n, 8), 256), 256, dT, n, code, bits, k0, sb.k[0]);
     }
-    rc = radix_sort(ctx, st, sb, n, P0, true);
+    rc = radix_sort(ctx, st, sb, n, P0, true, false);
     if (rc) return rc;
 
     CK(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
@@ -432,15 +442,18 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             sortedS = true;
         }
         if (mL) {
+            const int passes = max(1, (int)cdiv((u64)kb + max(1, bit_length((u64)mL - 1)), 8));
+            rc = radix_prepare(ctx, st, sb);
+            if (rc) return rc;
+            const u32 bgrid = min(cdiv(mL, 256), 148u * 8u);
             if (!linear) {
-                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys, cdiv(mL, 256), 256, sb.v[sb.cur], gst[g], mL, rank, FS,
-                       cidx, (u32)k, kb, sb.k[sb.cur]);
+                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<false>, bgrid, 256, sb.v[sb.cur], gst[g], mL, rank, FS,
+                       cidx, n, (u32)k, kb, sb.k[sb.cur], passes, sb.hist);
             } else {
-                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys_linear, cdiv(mL, 256), 256, sb.v[sb.cur], gst[g], mL,
-                       rank, n, (u32)k, kb, sb.k[sb.cur]);
+                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<true>, bgrid, 256, sb.v[sb.cur], gst[g], mL, rank, FS,
+                       cidx, n, (u32)k, kb, sb.k[sb.cur], passes, sb.hist);
             }
-            const int passes = (int)cdiv((u64)kb + max(1, bit_length((u64)mL - 1)), 8);
-            rc = radix_sort(ctx, st, sb, mL, passes, false);
+            rc = radix_sort(ctx, st, sb, mL, passes, false, true);
             if (rc) return rc;
             sortedL = true;
         }

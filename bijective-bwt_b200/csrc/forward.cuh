@@ -107,38 +107,60 @@ __global__ void __launch_bounds__(256) k_init_keys_linear(const u8 *__restrict__
 }
 
 // ---- key build of one doubling round ---------------------------------------------------------
-// key[j] = gst[j] << kb | rank[succ^k(idx[j])]
+// key[j] = gst[j] << kb | rank[succ^k(idx[j])], and -- while the key is in a register and the
+// kernel waits on its random gather anyway -- the digit histograms of all radix passes
+// (same shared-memory scheme as k_radix_hist, which this replaces for the doubling rounds).
+// Grid-stride over warps of 32 slots; ghist: [8][256], zeroed by the host.
+template <bool LINEAR>
 __global__ void __launch_bounds__(256) k_build_keys(const u32 *__restrict__ idx, const u32 *__restrict__ gst, u32 m,
                                                     const u32 *__restrict__ rank, const u32 *__restrict__ FS,
-                                                    const u32 *__restrict__ cidx, u32 k, u32 kb,
-                                                    u64 *__restrict__ keys)
+                                                    const u32 *__restrict__ cidx, u32 n, u32 k, u32 kb,
+                                                    u64 *__restrict__ keys, int passes, u32 *__restrict__ ghist)
 {
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const u32 i = ldg_stream_u32(idx + j);
-    const u32 f = factor_of(FS, cidx, i);
-    const u32 s = __ldg(FS + f), len = __ldg(FS + f + 1) - s;
-    u32 o = i - s;
-    if (len > 1) {
-        const u32 kk = (k < len) ? k : k % len;
-        o += kk;                      // < 2 * len <= 2^31
-        if (o >= len) o -= len;
+    __shared__ u32 sh[8][256];
+    for (u32 i = threadIdx.x; i < 8 * 256; i += blockDim.x) ((u32 *)sh)[i] = 0;
+    __syncthreads();
+    const u32 lane = lane_id();
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 jb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); jb < m; jb += stride) {
+        const u32 j = jb + lane;
+        const bool valid = j < m;
+        u64 key = 0;
+        if (valid) {
+            const u32 i = ldg_stream_u32(idx + j);
+            u32 r;
+            if (LINEAR) {
+                const u64 t = (u64)i + k;
+                r = (t < n) ? __ldg(rank + (u32)t) + 1 : 0;
+            } else {
+                const u32 f = factor_of(FS, cidx, i);
+                const u32 s = __ldg(FS + f), len = __ldg(FS + f + 1) - s;
+                u32 o = i - s;
+                if (len > 1) {
+                    o += (k < len) ? k : k % len;  // < 2 * len <= 2^31
+                    if (o >= len) o -= len;
+                }
+                r = __ldg(rank + s + o);
+            }
+            key = ((u64)ldg_stream_u32(gst + j) << kb) | (u64)r;
+            keys[j] = key;
+        }
+        const bool whole = __all_sync(FULL_MASK, valid);
+        for (int p = 0; p < passes; p++) {
+            const u32 d = (u32)(key >> (p * 8)) & 255;
+            const u32 d0 = __shfl_sync(FULL_MASK, d, 0);
+            if (whole && __all_sync(FULL_MASK, d == d0)) {
+                if (lane == 0) atomicAdd(&sh[p][d0], 32u);
+            } else if (valid) {
+                atomicAdd(&sh[p][d], 1u);
+            }
+        }
     }
-    const u32 r = __ldg(rank + s + o);
-    keys[j] = ((u64)ldg_stream_u32(gst + j) << kb) | (u64)r;
-}
-
-// linear (suffix-array) variant: succ^k(i) = i + k, the end of the text is the smallest symbol
-__global__ void __launch_bounds__(256) k_build_keys_linear(const u32 *__restrict__ idx, const u32 *__restrict__ gst,
-                                                           u32 m, const u32 *__restrict__ rank, u32 n, u32 k, u32 kb,
-                                                           u64 *__restrict__ keys)
-{
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const u32 i = ldg_stream_u32(idx + j);
-    const u64 t = (u64)i + k;
-    const u32 r = (t < n) ? __ldg(rank + (u32)t) + 1 : 0;
-    keys[j] = ((u64)ldg_stream_u32(gst + j) << kb) | (u64)r;
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < (u32)passes * 256; i += blockDim.x) {
+        const u32 c = ((u32 *)sh)[i];
+        if (c) atomicAdd(ghist + i, c);
+    }
 }
 
 // ---- re-rank + compaction -----------------------------------------------------------------------
