@@ -143,7 +143,7 @@ static size_t workspace_bytes(size_t n)
 {
     // forward is the larger of the two: L set keys 2x8 + idx/grp/gst 2x4 each, S set keys 8 +
     // idx/grp/gst 2x4 each, rank 4, FS 4, flags 1, onesweep status n, misc
-    return n * 106 + (64u << 20);
+    return n * 114 + (64u << 20);
 }
 
 static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
@@ -244,6 +244,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     sb.status = arena_take<u64>(ctx, (size_t)os_tiles * RADIX_BINS);
     u32 *grp[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
     u32 *gst[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
+    u32 *gid[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};  // dense group index of the L set
     u32 *rank = arena_take<u32>(ctx, n);
     u32 *FS = arena_take<u32>(ctx, (size_t)n + 1);
     u32 *cidx = arena_take<u32>(ctx, (size_t)nblk + 2);
@@ -258,7 +259,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     u32 *small = arena_take<u32>(ctx, 1024);  // [0] F, [1] lmax, [2] sigma, [8..15] presence, [16..] rerank counters
     u8 *code = (u8 *)arena_take<u32>(ctx, 64);
     if (!sb.k[0] || !sb.k[1] || !sb.v[0] || !sb.v[1] || !sb.hist || !sb.status || !grp[0] || !grp[1] || !gst[0] ||
-        !gst[1] || !rank || !FS || !cidx || !flags || !tilecnt || !rr_statusA || !rr_statusB || !small || !code || !kS ||
+        !gst[1] || !gid[0] || !gid[1] || !rank || !FS || !cidx || !flags || !tilecnt || !rr_statusA || !rr_statusB || !small || !code || !kS ||
         !vS[0] || !vS[1] || !grpS[0] || !grpS[1] || !gstS[0] || !gstS[1])
         return BWTS_B200_EINTERNAL;
     RerankCounters *rrc = (RerankCounters *)(small + 16);
@@ -350,7 +351,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     // Two live sets.  L: groups of any size, sorted by the global radix path (sb, grp, gst).
     // S: groups of at most 32 members, sorted warp-locally (kS, vS, grpS, gstS).
     int g = 0, gs = 0, cs = 0;       // current buffers of grp/gst (L), grpS/gstS, vS
-    u32 mL = n, mS = 0, groups_before = 1;
+    u32 mL = n, mS = 0, groups_before = 1, groupsL = 0;
     u64 k = k0;
     const u32 kb = linear ? bit_length(n) : max(1, bit_length((u64)n - 1));
     bool first = true, sortedL = true;  // the L set enters the loop freshly sorted (initial sort)
@@ -358,20 +359,20 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     for (;;) {
         // ---- re-rank what was just sorted; S first, L appends to the same S stream
         CK(cudaMemsetAsync(rrc, 0, 2 * sizeof(RerankCounters), st));
-        LiveOut oS = {vS[cs], grpS[gs ^ 1], gstS[gs ^ 1]};
+        LiveOut oS = {vS[cs], grpS[gs ^ 1], gstS[gs ^ 1], nullptr};
         if (mS && sortedS) {
             CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
             CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
-            LiveOut none = {nullptr, nullptr, nullptr};
+            LiveOut none = {nullptr, nullptr, nullptr, nullptr};
             LAUNCH(KC_RERANK, 24.0 * mS, k_rerank<false>, cdiv(mS, RR_TILE), RR_NT, kS, vS[cs ^ 1], grpS[gs],
                    gstS[gs], mS, 0, rank, oS, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0);
         }
         if (mL && sortedL) {
             CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
             CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
-            LiveOut oL = {sb.v[sb.cur ^ 1], grp[g ^ 1], gst[g ^ 1]};
+            LiveOut oL = {sb.v[sb.cur ^ 1], grp[g ^ 1], gst[g ^ 1], gid[g ^ 1]};
             if (g_tune_local) {
-                LiveOut none = {nullptr, nullptr, nullptr};
+                LiveOut none = {nullptr, nullptr, nullptr, nullptr};
                 LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<false>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp[g], gst[g], mL, 0, rank, oL, (const u32 *)nullptr, none,
                        rr_statusA, rr_statusB, rrc + 1);
@@ -407,12 +408,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         mS = newS;
         mL = newL;
         groups_before = cS.kheads + cL.kheads;
+        groupsL = g_tune_local ? 0 : cL.kheadsL;
         if (mS + mL == 0) break;
         const bool deep_enough = !linear && k >= 2ull * lmax;  // Fine-Wilf: remaining ties are equal rotations
         if (!split || deep_enough) {
             if (linear) return BWTS_B200_EINTERNAL;  // suffixes are pairwise distinct
             // ties are final: give every member of a tie its own slot
-            LiveOut none = {nullptr, nullptr, nullptr};
+            LiveOut none = {nullptr, nullptr, nullptr, nullptr};
             if (mS) {
                 CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
@@ -442,15 +444,19 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             sortedS = true;
         }
         if (mL) {
-            const int passes = max(1, (int)cdiv((u64)kb + max(1, bit_length((u64)mL - 1)), 8));
+            // high part of the key: the dense group index (fewest bits); with routing off the
+            // group start offset does the same job
+            const u32 *hi = groupsL ? gid[g] : gst[g];
+            const int hibits = max(1, bit_length(groupsL ? (u64)groupsL - 1 : (u64)mL - 1));
+            const int passes = max(1, (int)cdiv((u64)kb + hibits, 8));
             rc = radix_prepare(ctx, st, sb);
             if (rc) return rc;
             const u32 bgrid = min(cdiv(mL, 256), 148u * 8u);
             if (!linear) {
-                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<false>, bgrid, 256, sb.v[sb.cur], gst[g], mL, rank, FS,
+                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<false>, bgrid, 256, sb.v[sb.cur], hi, mL, rank, FS,
                        cidx, n, (u32)k, kb, sb.k[sb.cur], passes, sb.hist);
             } else {
-                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<true>, bgrid, 256, sb.v[sb.cur], gst[g], mL, rank, FS,
+                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<true>, bgrid, 256, sb.v[sb.cur], hi, mL, rank, FS,
                        cidx, n, (u32)k, kb, sb.k[sb.cur], passes, sb.hist);
             }
             rc = radix_sort(ctx, st, sb, mL, passes, false, true);

@@ -107,12 +107,12 @@ __global__ void __launch_bounds__(256) k_init_keys_linear(const u8 *__restrict__
 }
 
 // ---- key build of one doubling round ---------------------------------------------------------
-// key[j] = gst[j] << kb | rank[succ^k(idx[j])], and -- while the key is in a register and the
+// key[j] = hi[j] << kb | rank[succ^k(idx[j])] (hi = dense group index, or gst), and -- while the key is in a register and the
 // kernel waits on its random gather anyway -- the digit histograms of all radix passes
 // (same shared-memory scheme as k_radix_hist, which this replaces for the doubling rounds).
 // Grid-stride over warps of 32 slots; ghist: [8][256], zeroed by the host.
 template <bool LINEAR>
-__global__ void __launch_bounds__(256) k_build_keys(const u32 *__restrict__ idx, const u32 *__restrict__ gst, u32 m,
+__global__ void __launch_bounds__(256) k_build_keys(const u32 *__restrict__ idx, const u32 *__restrict__ hi, u32 m,
                                                     const u32 *__restrict__ rank, const u32 *__restrict__ FS,
                                                     const u32 *__restrict__ cidx, u32 n, u32 k, u32 kb,
                                                     u64 *__restrict__ keys, int passes, u32 *__restrict__ ghist)
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_build_keys(const u32 *__restrict__ idx,
                 }
                 r = __ldg(rank + s + o);
             }
-            key = ((u64)ldg_stream_u32(gst + j) << kb) | (u64)r;
+            key = ((u64)ldg_stream_u32(hi + j) << kb) | (u64)r;  // hi: any index that grows with the group
             keys[j] = key;
         }
         const bool whole = __all_sync(FULL_MASK, valid);
@@ -177,12 +177,15 @@ __global__ void __launch_bounds__(256) k_build_keys(const u32 *__restrict__ idx,
 #define RR_FLAG_PREFIX 2ull
 #define RR_SMALL 32
 // status words: A = flag[63:62] | (last head position + 1)[61:31] | kept in S [30:0]
-//               B = flag[63:62] | kept in L [31:0]
+//               B = flag[63:62] | kept group heads in L [61:31] | kept in L [30:0]
 static __device__ __forceinline__ u64 rr_packA(u64 flag, u32 headp1, u32 keep)
 {
     return (flag << 62) | ((u64)headp1 << 31) | (u64)keep;
 }
-static __device__ __forceinline__ u64 rr_packB(u64 flag, u32 keep) { return (flag << 62) | (u64)keep; }
+static __device__ __forceinline__ u64 rr_packB(u64 flag, u32 heads, u32 keep)
+{
+    return (flag << 62) | ((u64)heads << 31) | (u64)keep;
+}
 
 struct RerankCounters {  // zeroed before each launch
     u32 ticket;
@@ -190,11 +193,13 @@ struct RerankCounters {  // zeroed before each launch
     u32 kheads;   // groups that stay live (both streams)
     u32 keptS;    // live elements compacted into the S stream
     u32 keptL;    // live elements compacted into the L stream
-    u32 pad[3];
+    u32 kheadsL;  // groups in the L stream
+    u32 pad[2];
 };
 
 struct LiveOut {  // one compaction stream
     u32 *idx, *grp, *gst;
+    u32 *gid;     // L stream only: dense index of the group inside the stream (radix key high part)
 };
 
 // grp == nullptr (with gst ignored): both arrays are all zero -- the first re-rank after the
@@ -211,8 +216,8 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
                                                   RerankCounters *__restrict__ ctr)
 {
     __shared__ u8 s_hb[RR_NT + 8];  // head flags of the tile, 8 slots per byte, + the slot after the tile
-    __shared__ u32 s_wh[RR_NT / 32], s_ws[RR_NT / 32], s_wl[RR_NT / 32];
-    __shared__ u32 s_tile, s_exh, s_exs, s_exl;
+    __shared__ u32 s_wh[RR_NT / 32], s_ws[RR_NT / 32], s_wl[RR_NT / 32], s_wg[RR_NT / 32];
+    __shared__ u32 s_tile, s_exh, s_exs, s_exl, s_exg;
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
         return w32 != 0;  // a head within 32 slots: the group has at most 32 members
     };
     u32 kbits = 0, sbits = 0;  // keep, keep-in-S
-    u32 lasth = 0, nS = 0, nL = 0, nhead = 0, nkhead = 0;
+    u32 lasth = 0, nS = 0, nL = 0, nG = 0, nhead = 0, nkhead = 0;  // nG: kept heads that go to L
     {
         // the group my first slot continues: its head is an earlier slot of this tile (or outside it)
         int route = -1;  // -1 unknown yet, 0 = L, 1 = S
@@ -327,45 +332,46 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
                         route = (hs >= 0 && group_small((u32)hs)) ? 1 : 0;
                     }
                     kbits |= 1u << q;
-                    if (route == 1) { sbits |= 1u << q; nS++; } else nL++;
+                    if (route == 1) { sbits |= 1u << q; nS++; } else { nL++; nG += h; }
                 }
             }
         }
     }
 
     // ---- block-wide scans of (max lasth, sum nS, sum nL)
-    const u32 ih = warp_incl_max(lasth), is = warp_incl_sum(nS), il = warp_incl_sum(nL);
-    if (lane == 31) { s_wh[warp] = ih; s_ws[warp] = is; s_wl[warp] = il; }
+    const u32 ih = warp_incl_max(lasth), is = warp_incl_sum(nS), il = warp_incl_sum(nL), ig = warp_incl_sum(nG);
+    if (lane == 31) { s_wh[warp] = ih; s_ws[warp] = is; s_wl[warp] = il; s_wg[warp] = ig; }
     const u32 th = warp_sum(nhead), tkh = warp_sum(nkhead);
     if (lane == 0 && (th | tkh)) { atomicAdd(&ctr->heads, th); atomicAdd(&ctr->kheads, tkh); }
     __syncthreads();
-    u32 offh = 0, offs = 0, offl = 0, toth = 0, tots = 0, totl = 0;
+    u32 offh = 0, offs = 0, offl = 0, offg = 0, toth = 0, tots = 0, totl = 0, totg = 0;
 #pragma unroll
     for (int w = 0; w < RR_NT / 32; w++) {
-        if (w < (int)warp) { offh = max(offh, s_wh[w]); offs += s_ws[w]; offl += s_wl[w]; }
+        if (w < (int)warp) { offh = max(offh, s_wh[w]); offs += s_ws[w]; offl += s_wl[w]; offg += s_wg[w]; }
         toth = max(toth, s_wh[w]);
         tots += s_ws[w];
         totl += s_wl[w];
+        totg += s_wg[w];
     }
 
     // ---- decoupled look-back on (max, sum, sum), by warp 0
     if (warp == 0) {
-        u32 exh = 0, exs = 0, exl = 0;
+        u32 exh = 0, exs = 0, exl = 0, exg = 0;
         if (tile == 0) {
             if (lane == 0) {
-                st_relaxed_u64(statusB, rr_packB(RR_FLAG_PREFIX, totl));
+                st_relaxed_u64(statusB, rr_packB(RR_FLAG_PREFIX, totg, totl));
                 st_relaxed_u64(statusA, rr_packA(RR_FLAG_PREFIX, toth, tots));
             }
         } else {
             if (lane == 0) {
-                st_relaxed_u64(statusB + tile, rr_packB(RR_FLAG_AGG, totl));
+                st_relaxed_u64(statusB + tile, rr_packB(RR_FLAG_AGG, totg, totl));
                 st_relaxed_u64(statusA + tile, rr_packA(RR_FLAG_AGG, toth, tots));
             }
             int t = (int)tile - 1;
             for (;;) {
                 const int q = t - (int)lane;
                 const u64 va = (q >= 0) ? ld_relaxed_u64(statusA + q) : rr_packA(RR_FLAG_PREFIX, 0, 0);
-                const u64 vb = (q >= 0) ? ld_relaxed_u64(statusB + q) : rr_packB(RR_FLAG_PREFIX, 0);
+                const u64 vb = (q >= 0) ? ld_relaxed_u64(statusB + q) : rr_packB(RR_FLAG_PREFIX, 0, 0);
                 const u32 fa = (u32)(va >> 62), fb = (u32)(vb >> 62);
                 // a tile counts once both of its words carry the same kind of flag
                 const u32 flag = (fa == fb) ? fa : 0u;
@@ -383,19 +389,21 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
                 const bool on = (take >> lane) & 1;
                 exh = max(exh, warp_max(on ? (u32)((va >> 31) & 0x7fffffffu) : 0u));
                 exs += warp_sum(on ? (u32)(va & 0x7fffffffu) : 0u);
-                exl += warp_sum(on ? (u32)vb : 0u);
+                exl += warp_sum(on ? (u32)(vb & 0x7fffffffu) : 0u);
+                exg += warp_sum(on ? (u32)((vb >> 31) & 0x7fffffffu) : 0u);
                 if (prefixes) break;
                 t -= 32;
             }
             if (lane == 0) {
-                st_relaxed_u64(statusB + tile, rr_packB(RR_FLAG_PREFIX, exl + totl));
+                st_relaxed_u64(statusB + tile, rr_packB(RR_FLAG_PREFIX, exg + totg, exl + totl));
                 st_relaxed_u64(statusA + tile, rr_packA(RR_FLAG_PREFIX, max(exh, toth), exs + tots));
             }
         }
         if (lane == 0) {
-            s_exh = exh; s_exs = exs; s_exl = exl;
+            s_exh = exh; s_exs = exs; s_exl = exl; s_exg = exg;
             if (tots) atomicAdd(&ctr->keptS, tots);
             if (totl) atomicAdd(&ctr->keptL, totl);
+            if (totg) atomicAdd(&ctr->kheadsL, totg);
         }
     }
     __syncthreads();
@@ -404,10 +412,12 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
     u32 eh = __shfl_up_sync(FULL_MASK, ih, 1);
     u32 es = __shfl_up_sync(FULL_MASK, is, 1);
     u32 el = __shfl_up_sync(FULL_MASK, il, 1);
-    if (lane == 0) { eh = 0; es = 0; el = 0; }
+    u32 eg = __shfl_up_sync(FULL_MASK, ig, 1);
+    if (lane == 0) { eh = 0; es = 0; el = 0; eg = 0; }
     u32 curh = max(s_exh, max(offh, eh));
     u32 curs = (baseS ? *baseS : 0u) + s_exs + offs + es;
     u32 curl = s_exl + offl + el;
+    u32 curg = s_exg + offg + eg;  // kept L heads up to and including the current slot
 #pragma unroll
     for (int q = 0; q < RR_IPT; q++) {
         if ((u32)q < mine) {
@@ -423,9 +433,11 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
                     outS.gst[curs] = curs - (j - jh);
                     curs++;
                 } else {
+                    curg += (hbits >> q) & 1;
                     outL.idx[curl] = vi[q];
                     outL.grp[curl] = nr;
                     outL.gst[curl] = curl - (j - jh);
+                    outL.gid[curl] = curg - 1;
                     curl++;
                 }
             }
