@@ -161,7 +161,7 @@ struct SortBufs {
     u64 *k[2];
     u32 *v[2];
     int cur;        // index of the buffers holding the data
-    u32 *hist;      // [8][256] + 8 tickets
+    u32 *hist;      // [8][256] (+ 8 spare words)
     u64 *status;    // tiles * 256
 };
 
@@ -176,7 +176,6 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
                       bool have_hist)
 {
     if (passes < 1 || passes > RADIX_MAX_PASSES) return BWTS_B200_EINTERNAL;
-    u32 *tickets = sb.hist + RADIX_MAX_PASSES * RADIX_BINS;
     if (!have_hist) {
         int rc0 = radix_prepare(ctx, st, sb);
         if (rc0) return rc0;
@@ -197,16 +196,16 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
         if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }           \
         k_onesweep_pass<NT_, IPT_, MINB_, LB_><<<cdiv(m, (NT_) * (IPT_)), NT_, OsSmem<NT_, IPT_>::bytes, st>>>( \
             sb.k[a], vin, sb.k[b], sb.v[b], m, (u32)(p * RADIX_BITS), sb.hist + p * RADIX_BINS, sb.status,  \
-            tickets + p, ctx->epoch);                                                                     \
+            ctx->epoch);                                                                                  \
         if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
         ctx->recs.push_back(r__);                                                                         \
         CK(cudaGetLastError());                                                                           \
     } while (0)
         switch (g_tune_onesweep) {
-        case 1: OS_LAUNCH(512, 8, 2, 16); break;
+        case 1: OS_LAUNCH(512, 8, 2, 8); break;
         case 2: OS_LAUNCH(1024, 8, 1, 8); break;
         case 3: OS_LAUNCH(256, 8, 4, 8); break;
-        default: OS_LAUNCH(512, 8, 2, 8); break;
+        default: OS_LAUNCH(384, 8, 3, 8); break;
         }
 #undef OS_LAUNCH
         sb.cur = b;
@@ -616,10 +615,10 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     cudaFuncSetAttribute(k_onesweep_pass<NT_, IPT_, MINB_, LB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                          (int)OsSmem<NT_, IPT_>::bytes);                                                         \
     cudaFuncSetAttribute(k_onesweep_pass<NT_, IPT_, MINB_, LB_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+    OS_ATTR(384, 8, 3, 8);
     OS_ATTR(512, 8, 2, 8);
     OS_ATTR(1024, 8, 1, 8);
     OS_ATTR(256, 8, 4, 8);
-    OS_ATTR(512, 8, 2, 16);
 #undef OS_ATTR
     bwts_b200_ctx *ctx = new bwts_b200_ctx();
     ctx->device = device;

@@ -1,7 +1,7 @@
 // radix.cuh -- LSD "onesweep" radix sort of (u64 key, u32 value) pairs, 8-bit digits.
 //
-// One launch per digit.  Each CTA takes the next tile from an atomic ticket, ranks its
-// keys with warp-level match masks into per-warp digit counters, publishes the tile's
+// One launch per digit.  CTA b owns tile b (tiles are dispatched in index order), ranks its
+// keys with warp-level ballot masks into per-warp digit counters, publishes the tile's
 // 256 digit counts, resolves its global offsets by decoupled look-back over the earlier
 // tiles' status words (single 64-bit words carrying epoch | flag | count, so no reset
 // between passes), stages keys and values through shared memory in tile-sorted order
@@ -21,6 +21,23 @@
 
 #define OS_FLAG_AGG 1ull
 #define OS_FLAG_PREFIX 2ull
+
+// per-phase cycle counters of the onesweep kernel: only tests/bench_onesweep.cu defines this
+#ifdef OS_PROFILE_PHASES
+__device__ unsigned long long g_os_phase[16];
+#define OS_PHASE_INIT() long long os_t_prev__ = clock64()
+#define OS_PHASE(i_)                                                            \
+    do {                                                                        \
+        if (threadIdx.x == 0) {                                                 \
+            const long long t__ = clock64();                                    \
+            atomicAdd(&g_os_phase[i_], (unsigned long long)(t__ - os_t_prev__)); \
+            os_t_prev__ = t__;                                                  \
+        }                                                                       \
+    } while (0)
+#else
+#define OS_PHASE_INIT() do { } while (0)
+#define OS_PHASE(i_) do { } while (0)
+#endif
 
 static __device__ __forceinline__ u64 os_pack(u32 epoch, u64 flag, u32 value)
 {
@@ -76,9 +93,23 @@ __global__ void __launch_bounds__(256) k_radix_hist_scan(u32 *__restrict__ ghist
 // ---- one onesweep pass -----------------------------------------------------------------
 // vin == nullptr means "values are the element indices" (first pass of the initial sort).
 // NT threads x IPT keys per thread = one tile; MINB = CTAs per SM the register budget allows;
-// LB = status words fetched per look-back step.  The look-back is the serial part of the
-// kernel (tiles/s <= LB / L2 latency), so it runs after keys and values have left the
-// registers for shared memory -- that staging needs only tile-local offsets.
+// LB = status words fetched per look-back step.
+//
+// Shape of the kernel, and what the per-phase cycle counters (OS_PROFILE_PHASES,
+// tests/bench_onesweep.cu) said about the first version (512 x 8, MATCH.ANY ranking, atomic
+// ticket, 29 k cycles per 4096-key tile on uniform digits):
+//   * ranking took 7.3 k cycles: MATCH.ANY occupies its unit for ~100 cycles per warp
+//     instruction when the 32 digits differ.  Peers are now the AND over the 8 digit bits of
+//     (ballot of the bit, complemented where my bit is 0): fixed cost, 4.1 k cycles.
+//   * the ticket (an exposed L2 atomic round trip, 1.6 k cycles) is gone: tile = blockIdx.x.
+//     CTAs are dispatched in index order -- the assumption cub::DeviceScan's look-back makes
+//     as well -- so every tile a look-back waits for is resident or finished.
+//   * the look-back (5.5 k cycles) is mostly a wait for the slowest of the ~85 predecessor
+//     tiles that have no prefix yet, not for status loads: windows of 16 or 32 words, a
+//     cooperative two-group window and a flag-word + 16-bit-aggregate-row protocol all
+//     measured slower or equal.  It runs after keys and values have left
+//     the registers for shared memory -- that staging needs only tile-local offsets.
+//   * three CTAs of 384 threads per SM (56 registers) overlap the phases better than two of 512.
 template <int NT, int IPT>
 struct OsSmem {
     static constexpr int TILE = NT * IPT, NW = NT / 32;
@@ -88,16 +119,14 @@ struct OsSmem {
     static constexpr size_t dstart = wcnt + sizeof(u16) * NW * RADIX_BINS;  // u32[256]
     static constexpr size_t adj = dstart + sizeof(u32) * RADIX_BINS;    // u32[256]
     static constexpr size_t wsum = adj + sizeof(u32) * RADIX_BINS;      // u32[8]
-    static constexpr size_t tile = wsum + sizeof(u32) * 8;              // u32
-    static constexpr size_t dig = tile + 16;                            // u8[TILE]
-    static constexpr size_t bytes = dig + TILE;
+    static constexpr size_t bytes = wsum + sizeof(u32) * 8;
 };
 
 template <int NT, int IPT, int MINB, int LB>
 __global__ void __launch_bounds__(NT, MINB)
 k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout,
                 u32 *__restrict__ vout, u32 m, u32 shift, const u32 *__restrict__ binbase,
-                u64 *__restrict__ status, u32 *__restrict__ ticket, u32 epoch)
+                u64 *__restrict__ status, u32 epoch)
 {
     using L = OsSmem<NT, IPT>;
     constexpr int TILE = L::TILE, NW = L::NW;
@@ -109,14 +138,13 @@ k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *_
     u32 *s_dstart = (u32 *)(smem + L::dstart);
     u32 *s_adj = (u32 *)(smem + L::adj);
     u32 *s_wsum = (u32 *)(smem + L::wsum);
-    u32 *s_tile = (u32 *)(smem + L::tile);
-    u8 *s_dig = smem + L::dig;
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) *s_tile = atomicAdd(ticket, 1u);
+    OS_PHASE_INIT();
     for (u32 i = tid; i < NW * RADIX_BINS / 2; i += NT) ((u32 *)s_wcnt)[i] = 0;
     __syncthreads();
-    const u32 tile = *s_tile;
+    OS_PHASE(0);
+    const u32 tile = blockIdx.x;
     const u32 base = tile * TILE;
     const u32 cnt = min((u32)TILE, m - base);
     const u32 wbase = base + warp * (32 * IPT);
@@ -134,26 +162,46 @@ k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *_
         const u32 g = wbase + j * 32 + lane;
         val[j] = (g < m) ? (vin ? ldg_stream_u32(vin + g) : g) : 0u;
     }
+#ifdef OS_PROFILE_PHASES
+    if (key[IPT - 1] == 0x123456789abcdefull && val[IPT - 1] == 0x1234567u) g_os_phase[15] = 1;  // wait for the loads
+#endif
+    OS_PHASE(1);
 
     // rank inside the warp, in slot order (stable)
     u16 *wc = s_wcnt[warp];
     const u32 lt = lanemask_lt();
     u16 rnk[IPT];
+    {
+        u32 peers[IPT];  // lanes whose digit equals mine
 #pragma unroll
-    for (int j = 0; j < IPT; j++) {
-        const u32 d = (u32)(key[j] >> shift) & (RADIX_BINS - 1);
-        const u32 peers = __match_any_sync(FULL_MASK, d);
-        const int leader = __ffs(peers) - 1;
-        u32 before = 0;
-        if ((int)lane == leader) {
-            before = wc[d];
-            wc[d] = (u16)(before + __popc(peers));
+        for (int j = 0; j < IPT; j++) {
+            const u32 dj = (u32)(key[j] >> shift) & (RADIX_BINS - 1);
+            u32 p = FULL_MASK;
+#pragma unroll
+            for (int b = 0; b < RADIX_BITS; b++) {
+                const u32 bit = (dj >> b) & 1u;
+                const u32 bal = __ballot_sync(FULL_MASK, bit);
+                p &= bal ^ (bit - 1u);  // lanes whose bit b equals mine
+            }
+            peers[j] = p;
         }
-        before = __shfl_sync(FULL_MASK, before, leader);
-        rnk[j] = (u16)(before + __popc(peers & lt));
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < IPT; j++) {
+            const u32 dj = (u32)(key[j] >> shift) & (RADIX_BINS - 1);
+            const int leader = __ffs(peers[j]) - 1;
+            u32 before = 0;
+            if ((int)lane == leader) {
+                before = wc[dj];
+                wc[dj] = (u16)(before + __popc(peers[j]));
+            }
+            before = __shfl_sync(FULL_MASK, before, leader);
+            rnk[j] = (u16)(before + __popc(peers[j] & lt));
+            __syncwarp();
+        }
     }
+    OS_PHASE(2);
     __syncthreads();
+    OS_PHASE(3);
 
     // one thread per digit: exclusive offsets of the warps, tile count, publish the aggregate
     u32 blockcnt = 0, dsum = 0;
@@ -179,6 +227,7 @@ k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *_
         s_dstart[d] = dsum;  // where the digit's run starts inside the sorted tile
     }
     __syncthreads();
+    OS_PHASE(4);
 
     // keys and values -> shared memory in tile-sorted order (frees their registers)
 #pragma unroll
@@ -187,8 +236,8 @@ k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *_
         const u32 pos = s_dstart[dj] + wc[dj] + rnk[j];
         s_keys[pos] = key[j];
         s_vals[pos] = val[j];
-        s_dig[pos] = (u8)dj;
     }
+    OS_PHASE(5);
 
     // decoupled look-back over the earlier tiles, LB status words per step
     if (tid < RADIX_BINS) {
@@ -219,16 +268,20 @@ k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *_
         }
         s_adj[d] = __ldg(binbase + d) + excl - dsum;
     }
+    OS_PHASE(6);
     __syncthreads();
+    OS_PHASE(7);
 
     // every digit run goes out with consecutive threads on consecutive addresses
 #pragma unroll
     for (int q = 0; q < IPT; q++) {
         const u32 s = q * NT + tid;
         if (s < cnt) {
-            const u32 dst = s + s_adj[s_dig[s]];
-            kout[dst] = s_keys[s];
+            const u64 k = s_keys[s];
+            const u32 dst = s + s_adj[(u32)(k >> shift) & (RADIX_BINS - 1)];
+            kout[dst] = k;
             vout[dst] = s_vals[s];
         }
     }
+    OS_PHASE(8);
 }
