@@ -36,6 +36,8 @@ WORKLOADS = {
     "C3F": ("fibonacci", 0, 256 << 20, "C3 stress: 256 MiB Fibonacci word"),
     # C5: a multi-block file of 8 x 256 MiB independent blocks (seeds 50..57) dealt over the ranks
     "C5": ("text", 50, 256 << 20, "C5: multi-block file, 8 x 256 MiB order-2 Markov text blocks"),
+    # the same shape at an eighth of the size (pipeline diagnostics)
+    "C5S": ("text", 50, 32 << 20, "C5 small: multi-block file, 8 x 32 MiB order-2 Markov text blocks"),
 }
 C5_BLOCKS = 8
 
@@ -49,13 +51,13 @@ def plan_blocks(workload, rank, world):
     """(generator kind, seed, bytes) of every block this rank transforms in one step.
     C1..C4: one block per rank (weak scaling).  C5: 8 fixed blocks dealt round-robin (strong)."""
     kind, seed, n, _ = WORKLOADS[workload]
-    if workload == "C5":
+    if workload in ("C5", "C5S"):
         return [(kind, seed + b, n) for b in range(C5_BLOCKS) if block_owner(b, world) == rank]
     return [(kind, seed + 100 * rank, n)]
 
 
 def total_blocks(workload, world):
-    return C5_BLOCKS if workload == "C5" else world
+    return C5_BLOCKS if workload in ("C5", "C5S") else world
 DOMINANT = "onesweep_pass"
 
 
@@ -239,7 +241,7 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": "bwts_round_trip_throughput", "value": value, "unit": "MB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.workload == "C5" else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if args.workload in ("C5", "C5S") else "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": desc + ", forward + inverse round trip", "bytes_per_gpu": n * blocks // world,
                    "blocks": blocks, "sample_bytes": sample},
@@ -369,21 +371,45 @@ def run_gpu_arm(args, rank, local_rank, world):
         e2e_step()
     barrier()
     e2e = [e2e_step() for _ in range(args.steps)]
-    clocks = sampler.stop()  # sampled across both timed regions (device-resident and end-to-end)
-    barrier()
     e2e_wall_ms = sum(w for w, _ in e2e) / args.steps
     e2e_dev_ms = sum(d for _, d in e2e) / args.steps
     for b in blocks:
         assert torch.equal(b["host_back"], b["host_in"]), "e2e round trip lost data"
+
+    # ---- several blocks per GPU: the block pipeline (bwts_b200_*_blocks: H2D of block b+1 |
+    # transform of block b | D2H of block b-1), whole call timed on the host clock
+    pipe_ms = None
+    if len(blocks) > 1 and len({b["n"] for b in blocks}) == 1:
+        nb_, bl = len(blocks), blocks[0]["n"]
+        cat_in = torch.cat([b["host_in"] for b in blocks]).pin_memory()
+        cat_mid = torch.empty_like(cat_in).pin_memory()
+        cat_back = torch.empty_like(cat_in).pin_memory()
+
+        def pipe_step():
+            t0 = time.perf_counter()
+            bwts.blocks_ptr(0, cat_in.data_ptr(), nb_ * bl, bl, cat_mid.data_ptr(), devices=[local_rank])
+            bwts.blocks_ptr(1, cat_mid.data_ptr(), nb_ * bl, bl, cat_back.data_ptr(), devices=[local_rank])
+            return (time.perf_counter() - t0) * 1e3
+
+        for _ in range(min(args.warmup, 1)):
+            pipe_step()
+        barrier()
+        pipe_ms = sum(pipe_step() for _ in range(args.steps)) / args.steps
+        assert torch.equal(cat_back, cat_in), "pipelined e2e round trip lost data"
+        for i, b in enumerate(blocks):
+            assert torch.equal(cat_mid[i * bl:(i + 1) * bl], b["host_mid"]), "pipelined forward differs from the per-block call"
+        del cat_in, cat_mid, cat_back
+    clocks = sampler.stop()  # sampled across the timed regions (device-resident and end-to-end)
+    barrier()
     data, d_mid = blocks[0]["data"], blocks[0]["d_mid"]
 
     # ---- max over ranks (times), sum over ranks (bytes)
-    t = torch.tensor([total_ms, fwd_ms, inv_ms, e2e_wall_ms, e2e_dev_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, fwd_ms, inv_ms, e2e_wall_ms, e2e_dev_ms, pipe_ms or 0.0], dtype=torch.float64, device=dev)
     nb = torch.tensor([float(my_bytes)], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(nb, op=dist.ReduceOp.SUM)
-    total_ms, fwd_ms, inv_ms, e2e_wall_ms, e2e_dev_ms = t.tolist()
+    total_ms, fwd_ms, inv_ms, e2e_wall_ms, e2e_dev_ms, pipe_ms_max = t.tolist()
     job_bytes = nb.item()
     ms_per_step = total_ms / args.steps
 
@@ -401,12 +427,12 @@ def run_gpu_arm(args, rank, local_rank, world):
         line = {
             "metric": "bwts_round_trip_throughput", "value": job_bytes / MB / (ms_per_step * 1e-3), "unit": "MB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong" if args.workload == "C5" else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if args.workload in ("C5", "C5S") else "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": desc + ", forward + inverse round trip", "bytes_per_gpu": my_bytes,
                        "blocks": total_blocks(args.workload, world), "l2": "flushed between steps (256 MiB device memset inside the timed loop)",
                        "generator": f"bijective-bwt_b200/host/gen_input.c kind={kind_name} seed={seed}"
-                                    + ("+block" if args.workload == "C5" else "+100*rank"),
+                                    + ("+block" if args.workload in ("C5", "C5S") else "+100*rank"),
                        "parallelism": f"independent blocks over {world} GPU(s), round-robin, no collective"},
             "forward_mbs": job_bytes / MB / (fwd_ms * 1e-3), "inverse_mbs": job_bytes / MB / (inv_ms * 1e-3),
             "forward_ms": fwd_ms, "inverse_ms": inv_ms,
@@ -433,6 +459,14 @@ def run_gpu_arm(args, rank, local_rank, world):
                           "live_sum": last_f["live_sum"], "cycles": last_i["factors"],
                           "splitters": last_i["splitters"], "unreached": last_i["unreached"]},
         }
+        if pipe_ms is not None:
+            # the headline end-to-end number of a multi-block workload is the pipelined call
+            line["e2e"]["one_block_at_a_time_value"] = line["e2e"]["value"]
+            line["e2e"]["value"] = job_bytes / MB / (pipe_ms_max * 1e-3)
+            line["e2e"]["wall_value"] = line["e2e"]["value"]
+            line["e2e"]["how"] = ("bwts_b200_forward_blocks + bwts_b200_inverse_blocks over all blocks of the rank, "
+                                  "pinned host buffers, per-device pipeline H2D | transform | D2H; host clock around "
+                                  "both calls (one_block_at_a_time_value: the per-block host-buffer calls, CUDA events)")
         if world == 1 and not args.no_cpu:
             kind = ref_kind()
             sample = min(n, args.cpu_sample)

@@ -146,6 +146,13 @@ def inverse_blocks(data, block_len, devices=(0,)):
     return _blocks(lib().bwts_b200_inverse_blocks, "bwts_b200_inverse_blocks", data, block_len, list(devices))
 
 
+def blocks_ptr(direction, in_ptr, length, block_len, out_ptr, devices=(0,)):
+    """bwts_b200_{forward,inverse}_blocks on raw host pointers (pinned buffers take the direct-copy path)."""
+    fn = lib().bwts_b200_inverse_blocks if direction else lib().bwts_b200_forward_blocks
+    devs = (ctypes.c_int * len(devices))(*devices)
+    _check(fn(in_ptr, length, block_len, out_ptr, devs, len(devices)), "bwts_b200_*_blocks")
+
+
 def suffix_array(data, device=0):
     """bwts_b200_divsufsort: suffix array (int32) of `data`."""
     src = _as_u8(data)

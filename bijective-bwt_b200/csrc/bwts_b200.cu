@@ -50,7 +50,8 @@ struct bwts_b200_ctx {
     size_t arena_bytes = 0, arena_used = 0;
     u8 *io_in = nullptr;     // host-buffer API: start of the I/O region at the bottom of the arena (while a call runs)
     size_t io_bytes = 0;
-    u32 *h_small = nullptr;  // pinned, 4 KiB, for counter read-backs
+    u32 *h_small = nullptr;  // pinned + mapped, 4 KiB, for counter read-backs
+    u32 *h_small_dev = nullptr;  // its device-side address
     int last_cuda = 0;
     bool profile = true;
     std::vector<LaunchRec> recs;
@@ -149,9 +150,19 @@ static size_t workspace_bytes(size_t n)
 static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
 static inline int bit_length(u64 v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
 
+// Counter read-backs go through a kernel that stores into mapped pinned memory, not through a
+// D2H memcpy: a memcpy would queue on the copy engine behind the block pipeline's bulk
+// transfers (up to 5 ms per read-back with 256 MiB blocks in flight).
+__global__ void k_readback(const u32 *__restrict__ src, u32 *__restrict__ host_dst, u32 words)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) host_dst[i] = src[i];
+}
 static int readback(bwts_b200_ctx *ctx, cudaStream_t st, const void *dptr, size_t bytes)
 {
-    CK(cudaMemcpyAsync(ctx->h_small, dptr, bytes, cudaMemcpyDeviceToHost, st));
+    const u32 words = (u32)((bytes + 3) / 4);
+    k_readback<<<cdiv(words, 128), 128, 0, st>>>((const u32 *)dptr, ctx->h_small_dev, words);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
 }
@@ -624,7 +635,8 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     ctx->device = device;
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaHostAlloc((void **)&ctx->h_small, 4096, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->h_small, 4096, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&ctx->h_small_dev, ctx->h_small, 0) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_begin) != cudaSuccess || cudaEventCreate(&ctx->ev_end) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_io0) != cudaSuccess || cudaEventCreate(&ctx->ev_io1) != cudaSuccess) {
         bwts_b200_destroy(ctx);
@@ -689,6 +701,10 @@ extern "C" int bwts_b200_inverse_device(bwts_b200_ctx *ctx, const void *d_in, lo
     return run_device(ctx, 1, d_in, len, d_out, stream);
 }
 
+#define MAX_DEV 64
+static std::mutex g_dev_mutex[MAX_DEV];
+static bwts_b200_ctx *g_dev_ctx[MAX_DEV];
+
 static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, long len, unsigned char *out)
 {
     if (!ctx) return BWTS_B200_EINVAL;
@@ -730,9 +746,6 @@ extern "C" int bwts_b200_inverse_host(bwts_b200_ctx *ctx, const unsigned char *i
 }
 
 // ---- one-call entry points ---------------------------------------------------------------------------
-#define MAX_DEV 64
-static std::mutex g_dev_mutex[MAX_DEV];
-static bwts_b200_ctx *g_dev_ctx[MAX_DEV];
 
 static int with_default_ctx(int device, int direction, const unsigned char *in, long len, unsigned char *out)
 {
@@ -756,6 +769,205 @@ extern "C" int bwts_b200_inverse(const unsigned char *in, long len, unsigned cha
     return with_default_ctx(device, 1, in, len, out);
 }
 
+// ---- independent blocks: per device a three-stage pipeline ------------------------------------------
+// SURVEY.md 8f row 1 (the steps either side of the hot path: map_file.c:16-46 before it,
+// mk_bwts_sa.c:60 / unbwts.c:173 after it).  For the blocks dealt to one device:
+//     loader    host bytes -> pinned chunk ring -> H2D on its own stream      (block b+1)
+//     compute   the transform on the context's stream                        (block b)
+//     drainer   D2H on its own stream -> pinned chunk ring -> caller's bytes  (block b-1)
+// Two device input and two device output buffers; counting semaphores hand blocks from stage
+// to stage.  Caller buffers that are already pinned (cudaHostAlloc / cudaHostRegister) skip the
+// chunk rings and are copied directly.  tune(5, 1) turns the overlap off (one block at a time).
+#include <condition_variable>
+
+struct Sema {
+    std::mutex m;
+    std::condition_variable cv;
+    long count;
+    explicit Sema(long c) : count(c) {}
+    void release() { { std::lock_guard<std::mutex> l(m); count++; } cv.notify_one(); }
+    void acquire() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return count > 0; }); count--; }
+};
+
+#define PIPE_CHUNK ((size_t)8 << 20)
+#define PIPE_NCHUNK 4
+
+static bool host_ptr_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+struct PinnedRing {
+    u8 *buf[PIPE_NCHUNK] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[PIPE_NCHUNK] = {nullptr, nullptr, nullptr, nullptr};
+    bool busy[PIPE_NCHUNK] = {false, false, false, false};
+    int init()
+    {
+        for (int i = 0; i < PIPE_NCHUNK; i++) {
+            if (cudaHostAlloc((void **)&buf[i], PIPE_CHUNK, cudaHostAllocDefault) != cudaSuccess) return BWTS_B200_ENOMEM;
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return BWTS_B200_ECUDA;
+        }
+        return 0;
+    }
+    void destroy()
+    {
+        for (int i = 0; i < PIPE_NCHUNK; i++) {
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            if (buf[i]) cudaFreeHost(buf[i]);
+        }
+    }
+};
+
+// host -> device, through the ring when the source is pageable; returns after the copies are ISSUED
+static int pipe_h2d(PinnedRing &ring, bool pinned, u8 *d_dst, const u8 *src, size_t len, cudaStream_t st, size_t &seq)
+{
+    if (pinned) return cudaMemcpyAsync(d_dst, src, len, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : BWTS_B200_ECUDA;
+    for (size_t off = 0; off < len; off += PIPE_CHUNK, seq++) {
+        const int c = (int)(seq % PIPE_NCHUNK);
+        const size_t l = len - off < PIPE_CHUNK ? len - off : PIPE_CHUNK;
+        if (ring.busy[c] && cudaEventSynchronize(ring.ev[c]) != cudaSuccess) return BWTS_B200_ECUDA;
+        memcpy(ring.buf[c], src + off, l);
+        if (cudaMemcpyAsync(d_dst + off, ring.buf[c], l, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaEventRecord(ring.ev[c], st) != cudaSuccess)
+            return BWTS_B200_ECUDA;
+        ring.busy[c] = true;
+    }
+    return 0;
+}
+
+// device -> host, complete on return; the copy of chunk i+1 runs while chunk i is moved to the caller's buffer
+static int pipe_d2h(PinnedRing &ring, bool pinned, u8 *dst, const u8 *d_src, size_t len, cudaStream_t st)
+{
+    if (pinned) {
+        if (cudaMemcpyAsync(dst, d_src, len, cudaMemcpyDeviceToHost, st) != cudaSuccess) return BWTS_B200_ECUDA;
+        return cudaStreamSynchronize(st) == cudaSuccess ? 0 : BWTS_B200_ECUDA;
+    }
+    const size_t nch = (len + PIPE_CHUNK - 1) / PIPE_CHUNK;
+    for (size_t i = 0; i <= nch; i++) {
+        if (i < nch) {
+            const int c = (int)(i % PIPE_NCHUNK);
+            const size_t off = i * PIPE_CHUNK, l = len - off < PIPE_CHUNK ? len - off : PIPE_CHUNK;
+            if (cudaMemcpyAsync(ring.buf[c], d_src + off, l, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaEventRecord(ring.ev[c], st) != cudaSuccess)
+                return BWTS_B200_ECUDA;
+        }
+        if (i >= 1) {  // chunk i-1 has been in flight while chunk i was issued
+            const int c = (int)((i - 1) % PIPE_NCHUNK);
+            const size_t off = (i - 1) * PIPE_CHUNK, l = len - off < PIPE_CHUNK ? len - off : PIPE_CHUNK;
+            if (cudaEventSynchronize(ring.ev[c]) != cudaSuccess) return BWTS_B200_ECUDA;
+            memcpy(dst + off, ring.buf[c], l);
+        }
+    }
+    return 0;
+}
+
+static long g_tune_pipeline = 0;  // 1 = no overlap between blocks on one device
+
+// all blocks b = first, first + stride, ... < nblocks on device `dev`
+static int run_blocks_on_device(int direction, const u8 *in, long len, long block_len, u8 *out, int dev, long first,
+                                long stride, long nblocks)
+{
+    std::vector<long> mine;
+    for (long b = first; b < nblocks; b += stride) mine.push_back(b);
+    if (mine.empty()) return 0;
+    if (dev >= MAX_DEV) return BWTS_B200_EINVAL;
+    // the device's cached context (and its workspace) serves all blocks of this call
+    std::lock_guard<std::mutex> lock(g_dev_mutex[dev]);
+    if (!g_dev_ctx[dev]) g_dev_ctx[dev] = bwts_b200_create(dev);
+    bwts_b200_ctx *ctx = g_dev_ctx[dev];
+    if (!ctx) return BWTS_B200_ENODEV;
+    if (cudaSetDevice(dev) != cudaSuccess) return BWTS_B200_ECUDA;
+    auto blk_off = [&](long b) { return b * block_len; };
+    auto blk_len = [&](long b) { return (blk_off(b) + block_len <= len) ? block_len : len - blk_off(b); };
+
+    if (g_tune_pipeline == 1 || mine.size() == 1) {
+        int rc = 0;
+        for (size_t i = 0; i < mine.size() && rc == 0; i++)
+            rc = run_host(ctx, direction, in + blk_off(mine[i]), blk_len(mine[i]), out + blk_off(mine[i]));
+        return rc;
+    }
+
+    const bool in_pinned = host_ptr_is_pinned(in), out_pinned = host_ptr_is_pinned(out);
+    const size_t slot_bytes = ((size_t)block_len + 255) & ~(size_t)255;
+    u8 *d_io = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_loaded[2] = {nullptr, nullptr};
+    PinnedRing ring_in, ring_out;
+    std::atomic<int> status{0};
+    auto fail = [&](int rc) { int z = 0; status.compare_exchange_strong(z, rc); };
+
+    int rc = arena_reserve(ctx, workspace_bytes((size_t)block_len));
+    if (rc == 0 && cudaMalloc((void **)&d_io, 4 * slot_bytes) != cudaSuccess) { cudaGetLastError(); rc = BWTS_B200_ENOMEM; }
+    if (rc == 0 && (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ev_loaded[0], cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ev_loaded[1], cudaEventDisableTiming) != cudaSuccess))
+        rc = BWTS_B200_ECUDA;
+    if (rc == 0 && !in_pinned) rc = ring_in.init();
+    if (rc == 0 && !out_pinned) rc = ring_out.init();
+    if (rc == 0) {
+        u8 *d_in[2] = {d_io, d_io + slot_bytes}, *d_out[2] = {d_io + 2 * slot_bytes, d_io + 3 * slot_bytes};
+        Sema in_free(2), in_ready(0), out_free(2), out_ready(0);
+        const size_t K = mine.size();
+
+        std::thread loader([&]() {
+            cudaSetDevice(dev);
+            size_t seq = 0;
+            for (size_t i = 0; i < K; i++) {
+                in_free.acquire();
+                if (status.load() == 0) {
+                    const long b = mine[i];
+                    int r = pipe_h2d(ring_in, in_pinned, d_in[i & 1], in + blk_off(b), (size_t)blk_len(b), s_in, seq);
+                    if (r == 0 && cudaEventRecord(ev_loaded[i & 1], s_in) != cudaSuccess) r = BWTS_B200_ECUDA;
+                    if (r) fail(r);
+                }
+                in_ready.release();
+            }
+        });
+        std::thread drainer([&]() {
+            cudaSetDevice(dev);
+            for (size_t i = 0; i < K; i++) {
+                out_ready.acquire();
+                if (status.load() == 0) {
+                    const long b = mine[i];
+                    const int r = pipe_d2h(ring_out, out_pinned, out + blk_off(b), d_out[i & 1], (size_t)blk_len(b), s_out);
+                    if (r) fail(r);
+                }
+                out_free.release();
+            }
+        });
+        // compute stage on this thread
+        cudaStream_t st = ctx->own_stream;
+        for (size_t i = 0; i < K; i++) {
+            in_ready.acquire();
+            out_free.acquire();
+            if (status.load() == 0) {
+                const long b = mine[i];
+                int r = 0;
+                if (cudaStreamWaitEvent(st, ev_loaded[i & 1], 0) != cudaSuccess) r = BWTS_B200_ECUDA;
+                if (r == 0) r = run_device(ctx, direction, d_in[i & 1], blk_len(b), d_out[i & 1], nullptr);
+                if (r) fail(r);
+            }
+            in_free.release();
+            out_ready.release();
+        }
+        loader.join();
+        drainer.join();
+        rc = status.load();
+    }
+    cudaDeviceSynchronize();
+    ring_in.destroy();
+    ring_out.destroy();
+    if (ev_loaded[0]) cudaEventDestroy(ev_loaded[0]);
+    if (ev_loaded[1]) cudaEventDestroy(ev_loaded[1]);
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+    if (d_io) cudaFree(d_io);
+    return rc;
+}
+
 static int run_blocks(int direction, const unsigned char *in, long len, long block_len, unsigned char *out,
                       const int *devices, int ndev)
 {
@@ -772,21 +984,10 @@ static int run_blocks(int direction, const unsigned char *in, long len, long blo
     const long nblocks = (len + block_len - 1) / block_len;
     std::vector<int> status(ndev, 0);
     std::vector<std::thread> workers;
-    for (int w = 0; w < ndev; w++) {
+    for (int w = 0; w < ndev; w++)
         workers.emplace_back([&, w]() {
-            bool any = false;
-            for (long b = w; b < nblocks; b += ndev) { any = true; break; }
-            if (!any) return;
-            bwts_b200_ctx *ctx = bwts_b200_create(dev[w]);
-            if (!ctx) { status[w] = BWTS_B200_ENODEV; return; }
-            for (long b = w; b < nblocks && status[w] == 0; b += ndev) {
-                const long o = b * block_len;
-                const long l = (o + block_len <= len) ? block_len : len - o;
-                status[w] = run_host(ctx, direction, in + o, l, out + o);
-            }
-            bwts_b200_destroy(ctx);
+            status[w] = run_blocks_on_device(direction, in, len, block_len, out, dev[w], w, ndev, nblocks);
         });
-    }
     for (std::thread &t : workers) t.join();
     for (int w = 0; w < ndev; w++)
         if (status[w]) return status[w];
@@ -879,5 +1080,6 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 3) { g_tune_local = value; return 0; }
     if (key == 4) { g_tune_lyndon = value; return 0; }
     if (key == 2) { if (value < 0 || value > 3) return BWTS_B200_EINVAL; g_tune_onesweep = value; return 0; }
+    if (key == 5) { g_tune_pipeline = value; return 0; }
     return BWTS_B200_EINVAL;
 }

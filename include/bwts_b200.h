@@ -57,8 +57,10 @@ int bwts_b200_inverse(const unsigned char *in, long len, unsigned char *out, int
 
 /* Independent blocks of `block_len` bytes (last one shorter), block j = bytes
  * [j*block_len, min((j+1)*block_len, len)); output block j = transform of input block
- * j at the same offsets.  Blocks are dealt round-robin over devices[0..ndev) with one
- * host thread and one stream per device; no inter-GPU traffic.  block_len <= 0 or
+ * j at the same offsets.  Blocks are dealt round-robin over devices[0..ndev); per device
+ * a three-stage pipeline (pinned staging + H2D of block b+1 | transform of block b | D2H
+ * + un-staging of block b-1, each on its own stream and host thread) overlaps the copies
+ * with the kernels; no inter-GPU traffic.  block_len <= 0 or
  * >= len means "whole input is one block" (= the reference's behaviour).
  * devices == NULL means devices 0..ndev-1.                                           */
 int bwts_b200_forward_blocks(const unsigned char *in, long len, long block_len,
@@ -124,8 +126,8 @@ const char *bwts_b200_version(void);
 /* Test hooks: override tuning constants so that small inputs exercise the multi-tile /
  * multi-chunk paths.  key: 0 = Lyndon chunk bytes (>= 1), 1 = inverse splitter shift
  * (density 2^-(32-shift), 20..31), 2 = onesweep tile shape (0..3), 3 = disable the
- * warp-local sort path (1), 4 = force the suffix-sort fallback for the Lyndon boundaries (1).
- * value 0 = default.       */
+ * warp-local sort path (1), 4 = force the suffix-sort fallback for the Lyndon boundaries (1),
+ * 5 = no copy/compute overlap between the blocks of one device (1).  value 0 = default.  */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

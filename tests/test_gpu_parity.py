@@ -152,6 +152,45 @@ def test_blocks_equal_concatenated_single_blocks(bwts, oracle, gen):
     assert bwts.forward_blocks(x, 0) == oracle.forward(x)
 
 
+def test_block_pipeline_many_ragged_blocks(bwts, oracle, gen):
+    """per device: loader / compute / drainer overlap over many blocks; pageable buffers
+    go through the pinned chunk rings (blocks larger than one 8 MiB chunk and much smaller ones)"""
+    x = gen.make("text", 22, 1_234_567)
+    for b in (100_003, 65_536, 1_234_566):
+        want = b"".join(oracle.forward(x[o:o + b]) for o in range(0, len(x), b))
+        got = bwts.forward_blocks(x, b, devices=[0])
+        assert got == want, b
+        assert bwts.inverse_blocks(got, b, devices=[0]) == x, b
+    # overlap off (one block at a time) gives the same bytes
+    bwts.tune(5, 1)
+    try:
+        b = 100_003
+        assert bwts.forward_blocks(x, b, devices=[0]) == b"".join(
+            oracle.forward(x[o:o + b]) for o in range(0, len(x), b))
+    finally:
+        bwts.tune(5, 0)
+    # blocks that span several ring chunks
+    y = gen.make("dna", 23, 40_000_000)
+    b = 17_000_000
+    got = bwts.forward_blocks(y, b, devices=[0])
+    assert got == b"".join(oracle.forward(y[o:o + b]) for o in range(0, len(y), b))
+    assert bwts.inverse_blocks(got, b, devices=[0]) == y
+
+
+def test_block_pipeline_pinned_buffers(bwts, oracle, gen):
+    """pinned caller buffers are copied directly (no chunk ring)"""
+    import torch
+    x = gen.make("text", 24, 5_000_000)
+    b = 700_001
+    src = torch.frombuffer(bytearray(x), dtype=torch.uint8).pin_memory()
+    mid = torch.empty_like(src).pin_memory()
+    back = torch.empty_like(src).pin_memory()
+    bwts.blocks_ptr(0, src.data_ptr(), len(x), b, mid.data_ptr(), devices=[0])
+    assert bytes(mid.numpy()) == b"".join(oracle.forward(x[o:o + b]) for o in range(0, len(x), b))
+    bwts.blocks_ptr(1, mid.data_ptr(), len(x), b, back.data_ptr(), devices=[0])
+    assert bytes(back.numpy()) == x
+
+
 def test_one_call_entry_points_and_errors(bwts, oracle):
     x = b"abracadabra" * 1000
     assert bwts.forward(x) == oracle.forward(x)
