@@ -40,6 +40,7 @@ static long g_tune_spl_shift = 0;  // splitter shift   (0 = 26)
 static long g_tune_onesweep = 0;   // onesweep tile configuration (see radix_sort)
 static long g_tune_local = 0;      // 1 = never use the warp-local sort path
 static long g_tune_lyndon = 0;     // 1 = always take the suffix-sort fallback for the Lyndon boundaries
+static long g_tune_keybits = 0;    // cap on the bits of the initial packed key (0 = 64)
 
 struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; };
 
@@ -342,7 +343,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     }
     const u32 syms = linear ? sigma + 1 : sigma;  // linear mode reserves code 0 for "past the end"
     const u32 bits = max(1, bit_length(syms - 1));
-    const u32 k0 = 64 / bits;
+    const u32 keybits = (g_tune_keybits >= 8 && g_tune_keybits <= 64) ? (u32)g_tune_keybits : 64u;
+    const u32 k0 = max(1u, keybits / bits);
     const int P0 = (int)cdiv((u64)k0 * bits, 8);
     ctx->stats.alphabet_bits = (int)bits;
     ctx->stats.initial_depth = (int)k0;
@@ -1081,5 +1083,6 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 4) { g_tune_lyndon = value; return 0; }
     if (key == 2) { if (value < 0 || value > 3) return BWTS_B200_EINVAL; g_tune_onesweep = value; return 0; }
     if (key == 5) { g_tune_pipeline = value; return 0; }
+    if (key == 6) { g_tune_keybits = value; return 0; }
     return BWTS_B200_EINVAL;
 }

@@ -490,21 +490,44 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *__restrict__
             pay[h] = i;
         }
     }
-    // position = number of slots that order before mine (ties broken by slot number)
+    // Groups are contiguous runs of slots; a slot's position inside its group = number of
+    // members that order before it (ties broken by slot number).  The loop runs over the
+    // offset inside the group, so its trip count is the largest group of the warp (2-4 for
+    // DNA-like inputs), not the number of slots.
+    const u64 gmask = ((u64)1 << kb) - 1;
+    const bool head0 = (lane < cnt) && ((key[0] >> kb) == (u64)(lo + lane));
+    const bool head1 = (lane + 32 < cnt) && ((key[1] >> kb) == (u64)(lo + lane + 32));
+    const u64 H = (u64)__ballot_sync(FULL_MASK, head0) | ((u64)__ballot_sync(FULL_MASK, head1) << 32);
+    u32 gs[2], ge[2], r[2];
+    u32 maxlen = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const u32 s = lane + 32 * h;
+        const u64 upto = (s == 63) ? ~0ull : (((u64)2 << s) - 1);  // slots 0..s
+        const u64 below = H & upto, above = H & ~upto;
+        gs[h] = below ? 63u - (u32)__clzll((long long)below) : 0u;
+        ge[h] = above ? (u32)__ffsll((long long)above) - 1u : cnt;
+        r[h] = (u32)(key[h] & gmask);
+        if (s < cnt) maxlen = max(maxlen, ge[h] - gs[h]);
+    }
+    maxlen = warp_max(maxlen);
     u32 pos[2] = {0, 0};
-    for (u32 t = 0; t < cnt; t++) {
-        const u64 other = __shfl_sync(FULL_MASK, (t < 32) ? key[0] : key[1], t & 31);
+    for (u32 o = 0; o < maxlen; o++) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            const u32 t = gs[h] + o;  // a member of my group while t < ge
+            const u32 a = __shfl_sync(FULL_MASK, r[0], t & 31);
+            const u32 b = __shfl_sync(FULL_MASK, r[1], t & 31);
+            const u32 other = (t & 32) ? b : a;
             const u32 me = lane + 32 * h;
-            pos[h] += (other < key[h]) || (other == key[h] && t < me);
+            pos[h] += (t < ge[h]) && ((other < r[h]) || (other == r[h] && t < me));
         }
     }
 #pragma unroll
     for (int h = 0; h < 2; h++)
         if (lane + 32 * h < cnt) {
-            keys_out[lo + pos[h]] = key[h];
-            idx_out[lo + pos[h]] = pay[h];
+            keys_out[lo + gs[h] + pos[h]] = key[h];
+            idx_out[lo + gs[h] + pos[h]] = pay[h];
         }
 }
 
