@@ -41,6 +41,13 @@ static long g_tune_onesweep = 0;   // onesweep tile configuration (see radix_sor
 static long g_tune_local = 0;      // 1 = never use the warp-local sort path
 static long g_tune_lyndon = 0;     // 1 = always take the suffix-sort fallback for the Lyndon boundaries
 static long g_tune_keybits = 0;    // cap on the bits of the initial packed key (0 = 64)
+static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
+
+static bool use_binned_scatter(unsigned n, unsigned kb)
+{
+    if (g_tune_scatterbin == 1 || kb < 8) return false;
+    return g_tune_scatterbin == 2 || n >= (1u << 22);
+}
 
 struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; };
 
@@ -206,7 +213,7 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
         LaunchRec r__;                                                                                    \
         r__.cls = KC_ONESWEEP; r__.bytes = bytes; r__.e0 = r__.e1 = nullptr;                              \
         if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }           \
-        k_onesweep_pass<NT_, IPT_, MINB_, LB_><<<cdiv(m, (NT_) * (IPT_)), NT_, OsSmem<NT_, IPT_>::bytes, st>>>( \
+        k_onesweep_pass<u64, NT_, IPT_, MINB_, LB_><<<cdiv(m, (NT_) * (IPT_)), NT_, OsSmem<u64, NT_, IPT_>::bytes, st>>>( \
             sb.k[a], vin, sb.k[b], sb.v[b], m, (u32)(p * RADIX_BITS), sb.hist + p * RADIX_BINS, sb.status,  \
             ctx->epoch);                                                                                  \
         if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
@@ -377,22 +384,44 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
             LiveOut none = {nullptr, nullptr, nullptr, nullptr};
             LAUNCH(KC_RERANK, 24.0 * mS, k_rerank<false>, cdiv(mS, RR_TILE), RR_NT, kS, vS[cs ^ 1], grpS[gs],
-                   gstS[gs], mS, 0, rank, oS, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0);
+                   gstS[gs], mS, 0, rank, oS, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr);
         }
         if (mL && sortedL) {
             CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
             CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
             LiveOut oL = {sb.v[sb.cur ^ 1], grp[g ^ 1], gst[g ^ 1], gid[g ^ 1]};
+            // First re-rank of a large input: all n ranks are written, at random text positions
+            // (the kernel then runs at the DRAM random-access rate: 2.8 ms for 64 Mi elements, ncu:
+            // 85 B moved per element).  Instead the ranks go out in sorted order, one u32 onesweep
+            // pass bins the (position, rank) pairs by the top 8 bits of the position, and a
+            // streaming kernel scatters them region by region through L2.
+            const bool binned = first && use_binned_scatter(n, kb);
+            u32 *nr_out = binned ? (u32 *)sb.k[sb.cur ^ 1] : (u32 *)nullptr;  // the idle key buffer: 8n bytes
             if (g_tune_local) {
                 LiveOut none = {nullptr, nullptr, nullptr, nullptr};
                 LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<false>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp[g], gst[g], mL, 0, rank, oL, (const u32 *)nullptr, none,
-                       rr_statusA, rr_statusB, rrc + 1);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out);
             } else {
                 LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<true>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp[g], gst[g], mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL,
-                       rr_statusA, rr_statusB, rrc + 1);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out);
             }
+        }
+        if (mL && sortedL && first && use_binned_scatter(n, kb)) {
+            u32 *nr_buf = (u32 *)sb.k[sb.cur ^ 1], *bin_pos = nr_buf + (((size_t)n + 3) & ~(size_t)3), *bin_val = grp[g];  // 16-byte aligned; grp[g] is idle in the first round
+            const u32 shift = kb - 8;
+            LAUNCH(KC_RERANK, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
+            do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
+            LaunchRec r__;
+            r__.cls = KC_RERANK; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr;
+            if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
+            k_onesweep_pass<u32, 384, 8, 3, 8><<<cdiv(n, 384 * 8), 384, OsSmem<u32, 384, 8>::bytes, st>>>(
+                sb.v[sb.cur], nr_buf, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
+            if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
+            ctx->recs.push_back(r__);
+            CK(cudaGetLastError());
+            LAUNCH(KC_RERANK, 12.0 * n, k_scatter_pairs, cdiv(cdiv(n, 4), 256), 256, bin_pos, bin_val, n, rank);
         }
         rc = readback(ctx, st, rrc, 2 * sizeof(RerankCounters));
         if (rc) return rc;
@@ -432,7 +461,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                 CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
                 LAUNCH(KC_RERANK, 16.0 * mS, k_rerank<false>, cdiv(mS, RR_TILE), RR_NT, (const u64 *)nullptr, vS[cs],
-                       grpS[gs], gstS[gs], mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc);
+                       grpS[gs], gstS[gs], mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc,
+                       (u32 *)nullptr);
             }
             if (mL) {
                 CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
@@ -440,7 +470,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                 CK(cudaMemsetAsync(rrc + 1, 0, sizeof(RerankCounters), st));
                 LAUNCH(KC_RERANK, 16.0 * mL, k_rerank<false>, cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
                        sb.v[sb.cur], grp[g], gst[g], mL, 1, rank, none, (const u32 *)nullptr, none, rr_statusA,
-                       rr_statusB, rrc + 1);
+                       rr_statusB, rrc + 1, (u32 *)nullptr);
             }
             break;
         }
@@ -624,14 +654,15 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     if (device < 0 || device >= bwts_b200_device_count()) return nullptr;
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
     // the sort kernels use > 48 KB of dynamic shared memory and want the large carveout
-#define OS_ATTR(NT_, IPT_, MINB_, LB_)                                                                          \
-    cudaFuncSetAttribute(k_onesweep_pass<NT_, IPT_, MINB_, LB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                         (int)OsSmem<NT_, IPT_>::bytes);                                                         \
-    cudaFuncSetAttribute(k_onesweep_pass<NT_, IPT_, MINB_, LB_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-    OS_ATTR(384, 8, 3, 8);
-    OS_ATTR(512, 8, 2, 8);
-    OS_ATTR(1024, 8, 1, 8);
-    OS_ATTR(256, 8, 4, 8);
+#define OS_ATTR(K_, NT_, IPT_, MINB_, LB_)                                                                          \
+    cudaFuncSetAttribute(k_onesweep_pass<K_, NT_, IPT_, MINB_, LB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                         (int)OsSmem<K_, NT_, IPT_>::bytes);                                                         \
+    cudaFuncSetAttribute(k_onesweep_pass<K_, NT_, IPT_, MINB_, LB_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+    OS_ATTR(u64, 384, 8, 3, 8);
+    OS_ATTR(u64, 512, 8, 2, 8);
+    OS_ATTR(u64, 1024, 8, 1, 8);
+    OS_ATTR(u64, 256, 8, 4, 8);
+    OS_ATTR(u32, 384, 8, 3, 8);
 #undef OS_ATTR
     bwts_b200_ctx *ctx = new bwts_b200_ctx();
     ctx->device = device;
@@ -1084,5 +1115,6 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 2) { if (value < 0 || value > 3) return BWTS_B200_EINVAL; g_tune_onesweep = value; return 0; }
     if (key == 5) { g_tune_pipeline = value; return 0; }
     if (key == 6) { g_tune_keybits = value; return 0; }
+    if (key == 7) { g_tune_scatterbin = value; return 0; }
     return BWTS_B200_EINVAL;
 }

@@ -207,13 +207,16 @@ struct LiveOut {  // one compaction stream
 // ROUTE: decide S/L per group (otherwise everything kept goes to S, used for the S set itself).
 // finalize != 0: every element becomes its own group (ties are known to be final); no outputs.
 // baseS: device word holding the number of elements already in the S stream (nullptr = 0).
+// nr_out != nullptr: the new rank of slot j is stored at nr_out[j] instead of being scattered to
+// rank[idx[j]]; the caller bins the (idx, rank) pairs by text region and scatters them with
+// locality (first re-rank of large inputs, where every one of the n ranks is written).
 template <bool ROUTE>
 __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, const u32 *__restrict__ idx,
                                                   const u32 *__restrict__ grp, const u32 *__restrict__ gst, u32 m,
                                                   int finalize, u32 *__restrict__ rank, LiveOut outS,
                                                   const u32 *__restrict__ baseS, LiveOut outL,
                                                   u64 *__restrict__ statusA, u64 *__restrict__ statusB,
-                                                  RerankCounters *__restrict__ ctr)
+                                                  RerankCounters *__restrict__ ctr, u32 *__restrict__ nr_out)
 {
     __shared__ u8 s_hb[RR_NT + 8];  // head flags of the tile, 8 slots per byte, + the slot after the tile
     __shared__ u32 s_wh[RR_NT / 32], s_ws[RR_NT / 32], s_wl[RR_NT / 32], s_wg[RR_NT / 32];
@@ -425,7 +428,8 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
             if ((hbits >> q) & 1) curh = j + 1;
             const u32 jh = curh - 1;  // every slot has a head at or before it (slot gst[j] is one)
             const u32 nr = vg[q] + (jh - vs[q]);
-            if (nr != vg[q]) rank[vi[q]] = nr;
+            if (nr_out) nr_out[j] = nr;
+            else if (nr != vg[q]) rank[vi[q]] = nr;
             if ((kbits >> q) & 1) {
                 if ((sbits >> q) & 1) {
                     outS.idx[curs] = vi[q];
@@ -566,6 +570,30 @@ __global__ void __launch_bounds__(256) k_emit_sa(const u32 *__restrict__ rank, u
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) sa[ldg_stream_u32(rank + i)] = (i32)i;
+}
+
+// ---- binned rank scatter --------------------------------------------------------------------------
+// bin b of the binning pass = text positions [b << shift, (b + 1) << shift): every position occurs
+// exactly once among the n pairs, so the bin starts are known without counting
+__global__ void k_bin_bases(u32 n, u32 shift, u32 *__restrict__ base)
+{
+    const u64 start = (u64)threadIdx.x << shift;  // 256 threads
+    base[threadIdx.x] = (u32)min(start, (u64)n);
+}
+// rank[pos[j]] = val[j] over pairs that are grouped by text region: the targets of the CTAs
+// running at any one time fall into a few MiB, so the 4-byte stores merge in L2
+__global__ void __launch_bounds__(256) k_scatter_pairs(const u32 *__restrict__ pos, const u32 *__restrict__ val, u32 n,
+                                                       u32 *__restrict__ rank)
+{
+    const u32 j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= n) return;
+    if (j0 + 4 <= n) {
+        const uint4 p = ldg_stream_u4((const uint4 *)(pos + j0));
+        const uint4 v = ldg_stream_u4((const uint4 *)(val + j0));
+        rank[p.x] = v.x; rank[p.y] = v.y; rank[p.z] = v.z; rank[p.w] = v.w;
+    } else {
+        for (u32 j = j0; j < n; j++) rank[pos[j]] = val[j];
+    }
 }
 
 __global__ void k_set_u32(u32 *p, const u32 *idx_src, u32 value)

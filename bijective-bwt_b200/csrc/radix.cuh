@@ -110,11 +110,15 @@ __global__ void __launch_bounds__(256) k_radix_hist_scan(u32 *__restrict__ ghist
 //     measured slower or equal.  It runs after keys and values have left
 //     the registers for shared memory -- that staging needs only tile-local offsets.
 //   * three CTAs of 384 threads per SM (56 registers) overlap the phases better than two of 512.
-template <int NT, int IPT>
+static __device__ __forceinline__ u64 ldg_stream_key(const u64 *p) { return ldg_stream_u64(p); }
+static __device__ __forceinline__ u32 ldg_stream_key(const u32 *p) { return ldg_stream_u32(p); }
+
+// K = key type: u64 for the sorts of the doubling, u32 for the binning pass of the rank scatter
+template <typename K, int NT, int IPT>
 struct OsSmem {
     static constexpr int TILE = NT * IPT, NW = NT / 32;
-    static constexpr size_t keys = 0;                                   // u64[TILE]
-    static constexpr size_t vals = keys + sizeof(u64) * TILE;           // u32[TILE]
+    static constexpr size_t keys = 0;                                   // K[TILE]
+    static constexpr size_t vals = keys + sizeof(K) * TILE;             // u32[TILE]
     static constexpr size_t wcnt = vals + sizeof(u32) * TILE;           // u16[NW][256]
     static constexpr size_t dstart = wcnt + sizeof(u16) * NW * RADIX_BINS;  // u32[256]
     static constexpr size_t adj = dstart + sizeof(u32) * RADIX_BINS;    // u32[256]
@@ -122,17 +126,17 @@ struct OsSmem {
     static constexpr size_t bytes = wsum + sizeof(u32) * 8;
 };
 
-template <int NT, int IPT, int MINB, int LB>
+template <typename K, int NT, int IPT, int MINB, int LB>
 __global__ void __launch_bounds__(NT, MINB)
-k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout,
+k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__restrict__ kout,
                 u32 *__restrict__ vout, u32 m, u32 shift, const u32 *__restrict__ binbase,
                 u64 *__restrict__ status, u32 epoch)
 {
-    using L = OsSmem<NT, IPT>;
+    using L = OsSmem<K, NT, IPT>;
     constexpr int TILE = L::TILE, NW = L::NW;
     static_assert(NT >= RADIX_BINS && TILE <= 65536, "one thread per digit; 16-bit tile positions");
     extern __shared__ __align__(16) u8 smem[];
-    u64 *s_keys = (u64 *)(smem + L::keys);
+    K *s_keys = (K *)(smem + L::keys);
     u32 *s_vals = (u32 *)(smem + L::vals);
     u16(*s_wcnt)[RADIX_BINS] = (u16(*)[RADIX_BINS])(smem + L::wcnt);
     u32 *s_dstart = (u32 *)(smem + L::dstart);
@@ -150,12 +154,12 @@ k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *_
     const u32 wbase = base + warp * (32 * IPT);
 
     // warp-striped loads: slot j of lane l is tile position warp*32*IPT + j*32 + l
-    u64 key[IPT];
+    K key[IPT];
     u32 val[IPT];
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
         const u32 g = wbase + j * 32 + lane;
-        key[j] = (g < m) ? ldg_stream_u64(kin + g) : ~0ull;  // pads: digit 255, last in tile order
+        key[j] = (g < m) ? ldg_stream_key(kin + g) : (K)~(K)0;  // pads: digit 255, last in tile order
     }
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
@@ -163,7 +167,7 @@ k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *_
         val[j] = (g < m) ? (vin ? ldg_stream_u32(vin + g) : g) : 0u;
     }
 #ifdef OS_PROFILE_PHASES
-    if (key[IPT - 1] == 0x123456789abcdefull && val[IPT - 1] == 0x1234567u) g_os_phase[15] = 1;  // wait for the loads
+    if (key[IPT - 1] == (K)0x123456789abcdefull && val[IPT - 1] == 0x1234567u) g_os_phase[15] = 1;  // wait for the loads
 #endif
     OS_PHASE(1);
 
@@ -277,7 +281,7 @@ k_onesweep_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *_
     for (int q = 0; q < IPT; q++) {
         const u32 s = q * NT + tid;
         if (s < cnt) {
-            const u64 k = s_keys[s];
+            const K k = s_keys[s];
             const u32 dst = s + s_adj[(u32)(k >> shift) & (RADIX_BINS - 1)];
             kout[dst] = k;
             vout[dst] = s_vals[s];

@@ -86,8 +86,8 @@ static void run_kernel(const char *name, const void *kern, launcher_t launch, in
 template <int NT, int IPT, int MINB, int LB>
 static void run_config(const char *name, Bufs &b, u32 m, int reps, int dist)
 {
-    os_kernel_t kern = k_onesweep_pass<NT, IPT, MINB, LB>;
-    const size_t sm = OsSmem<NT, IPT>::bytes;
+    os_kernel_t kern = k_onesweep_pass<u64, NT, IPT, MINB, LB>;
+    const size_t sm = OsSmem<u64, NT, IPT>::bytes;
     run_kernel(name, (const void *)kern, [=](const u64 *ki, const u32 *vi, u64 *ko, u32 *vo, int p) {
         kern<<<(m + NT * IPT - 1) / (NT * IPT), NT, sm>>>(ki, vi, ko, vo, m, p * 8, b.hist + p * 256, b.status, g_epoch);
     }, NT, IPT, sm, b, m, reps, dist);

@@ -152,6 +152,27 @@ def test_blocks_equal_concatenated_single_blocks(bwts, oracle, gen):
     assert bwts.forward_blocks(x, 0) == oracle.forward(x)
 
 
+def test_binned_rank_scatter_forced_on_small_inputs(bwts, ctx, oracle, gen):
+    """first re-rank: ranks binned by text region with one u32 onesweep pass, then scattered
+    (default for >= 4 Mi bytes); forced here so that few-byte inputs cross the bin edges"""
+    bwts.tune(7, 2)
+    try:
+        for n in (256, 257, 1000, 3072, 3073, 70_001, 1 << 20):
+            for name, x in helpers.families(n).items():
+                assert ctx.forward_host(x) == oracle.forward(x), (name, n)
+        x = gen.make("text", 25, 3_000_001)
+        assert ctx.forward_host(x) == oracle.forward(x)
+        assert np.array_equal(bwts.suffix_array(x[:500_000]), oracle.suffix_array(x[:500_000]))
+    finally:
+        bwts.tune(7, 0)
+    bwts.tune(7, 1)
+    try:
+        x = gen.make("dna", 26, 5_000_000)
+        assert ctx.forward_host(x) == oracle.forward(x)
+    finally:
+        bwts.tune(7, 0)
+
+
 def test_block_pipeline_many_ragged_blocks(bwts, oracle, gen):
     """per device: loader / compute / drainer overlap over many blocks; pageable buffers
     go through the pinned chunk rings (blocks larger than one 8 MiB chunk and much smaller ones)"""
