@@ -427,6 +427,11 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         if (rc) return rc;
         const RerankCounters cS = ((const RerankCounters *)ctx->h_small)[0];
         const RerankCounters cL = ((const RerankCounters *)ctx->h_small)[1];
+        u32 headsS = 0, headsL = 0, kheadsS = 0, kheadsL_all = 0;
+        for (int q = 0; q < RR_SPREAD; q++) {
+            headsS += cS.heads[q]; headsL += cL.heads[q];
+            kheadsS += cS.kheads[q]; kheadsL_all += cL.kheads[q];
+        }
         if (first && !linear) {
             rc = readback(ctx, st, small + 1, 4);
             if (rc) return rc;
@@ -442,13 +447,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             newL = cL.keptL;
         }
         ctx->stats.class_bytes[KC_RERANK] += 12.0 * ((double)newS + newL);
-        const bool split = cS.heads + cL.heads != groups_before;
+        const bool split = headsS + headsL != groups_before;
         // adopt the compacted arrays
         if (mL && sortedL) { sb.cur ^= 1; g ^= 1; }   // idx of L now lives in sb.v[cur]
         if (!g_tune_local) gs ^= 1;                    // S stream was written to vS[cs], grpS/gstS[gs^1]
         mS = newS;
         mL = newL;
-        groups_before = cS.kheads + cL.kheads;
+        groups_before = kheadsS + kheadsL_all;
         groupsL = g_tune_local ? 0 : cL.kheadsL;
         if (mS + mL == 0) break;
         const bool deep_enough = !linear && k >= 2ull * lmax;  // Fine-Wilf: remaining ties are equal rotations

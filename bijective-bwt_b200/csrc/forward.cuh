@@ -187,14 +187,18 @@ static __device__ __forceinline__ u64 rr_packB(u64 flag, u32 heads, u32 keep)
     return (flag << 62) | ((u64)heads << 31) | (u64)keep;
 }
 
-struct RerankCounters {  // zeroed before each launch
-    u32 ticket;
-    u32 heads;    // groups after the split (all of them)
-    u32 kheads;   // groups that stay live (both streams)
-    u32 keptS;    // live elements compacted into the S stream
-    u32 keptL;    // live elements compacted into the L stream
-    u32 kheadsL;  // groups in the L stream
-    u32 pad[2];
+// Totals of one re-rank launch, zeroed before it.  heads / kheads are sums of per-tile counts:
+// one atomic per tile, spread over RR_SPREAD words (the ncu launch list showed the kernel at
+// 40 ns per tile with two same-address atomics per WARP: 0.5 M serialised L2 atomics per
+// launch).  The kept totals are the last tile's inclusive prefix: no atomics at all.
+#define RR_SPREAD 16
+struct RerankCounters {
+    u32 heads[RR_SPREAD];   // groups after the split (all of them)
+    u32 kheads[RR_SPREAD];  // groups that stay live (both streams)
+    u32 keptS;              // live elements compacted into the S stream
+    u32 keptL;              // live elements compacted into the L stream
+    u32 kheadsL;            // groups in the L stream
+    u32 pad[5];
 };
 
 struct LiveOut {  // one compaction stream
@@ -220,13 +224,15 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
 {
     __shared__ u8 s_hb[RR_NT + 8];  // head flags of the tile, 8 slots per byte, + the slot after the tile
     __shared__ u32 s_wh[RR_NT / 32], s_ws[RR_NT / 32], s_wl[RR_NT / 32], s_wg[RR_NT / 32];
-    __shared__ u32 s_tile, s_exh, s_exs, s_exl, s_exg;
+    __shared__ u32 s_nh[RR_NT / 32], s_nk[RR_NT / 32];
+    __shared__ u32 s_exh, s_exs, s_exl, s_exg;
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
     if (tid < 8) s_hb[RR_NT + tid] = 0;
     __syncthreads();
-    const u32 tile = s_tile, base = tile * RR_TILE;
+    // tile = blockIdx.x: CTAs are dispatched in index order, so the tiles a look-back waits for
+    // are resident or finished (same assumption as the onesweep kernel)
+    const u32 tile = blockIdx.x, base = tile * RR_TILE;
     const u32 j0 = base + tid * RR_IPT;
 
     // ---- my 8 slots, loaded up front (vector loads when the whole stretch is in range)
@@ -345,8 +351,15 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
     const u32 ih = warp_incl_max(lasth), is = warp_incl_sum(nS), il = warp_incl_sum(nL), ig = warp_incl_sum(nG);
     if (lane == 31) { s_wh[warp] = ih; s_ws[warp] = is; s_wl[warp] = il; s_wg[warp] = ig; }
     const u32 th = warp_sum(nhead), tkh = warp_sum(nkhead);
-    if (lane == 0 && (th | tkh)) { atomicAdd(&ctr->heads, th); atomicAdd(&ctr->kheads, tkh); }
+    if (lane == 0) { s_nh[warp] = th; s_nk[warp] = tkh; }
     __syncthreads();
+    if (tid == 0) {
+        u32 bh = 0, bk = 0;
+#pragma unroll
+        for (int w = 0; w < RR_NT / 32; w++) { bh += s_nh[w]; bk += s_nk[w]; }
+        if (bh) atomicAdd(&ctr->heads[tile % RR_SPREAD], bh);
+        if (bk) atomicAdd(&ctr->kheads[tile % RR_SPREAD], bk);
+    }
     u32 offh = 0, offs = 0, offl = 0, offg = 0, toth = 0, tots = 0, totl = 0, totg = 0;
 #pragma unroll
     for (int w = 0; w < RR_NT / 32; w++) {
@@ -404,48 +417,80 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
         }
         if (lane == 0) {
             s_exh = exh; s_exs = exs; s_exl = exl; s_exg = exg;
-            if (tots) atomicAdd(&ctr->keptS, tots);
-            if (totl) atomicAdd(&ctr->keptL, totl);
-            if (totg) atomicAdd(&ctr->kheadsL, totg);
+            if (tile == gridDim.x - 1) {  // the last tile's inclusive prefix = the totals
+                ctr->keptS = exs + tots;
+                ctr->keptL = exl + totl;
+                ctr->kheadsL = exg + totg;
+            }
         }
     }
     __syncthreads();
 
-    // ---- outputs
+    // ---- outputs.  Ranks: 8 consecutive slots per thread (vector store) or a scatter of the
+    // changed ones.  Compaction: through shared memory, S members packed from slot 0, L members
+    // behind them, so that both streams leave the tile with consecutive threads on consecutive
+    // addresses (per-thread runs cost 32 four-byte transactions per store instruction).
+    __shared__ u32 st_idx[RR_TILE], st_grp[RR_TILE], st_aux[RR_TILE], st_gid[RR_TILE];
     u32 eh = __shfl_up_sync(FULL_MASK, ih, 1);
     u32 es = __shfl_up_sync(FULL_MASK, is, 1);
     u32 el = __shfl_up_sync(FULL_MASK, il, 1);
     u32 eg = __shfl_up_sync(FULL_MASK, ig, 1);
     if (lane == 0) { eh = 0; es = 0; el = 0; eg = 0; }
     u32 curh = max(s_exh, max(offh, eh));
-    u32 curs = (baseS ? *baseS : 0u) + s_exs + offs + es;
-    u32 curl = s_exl + offl + el;
+    u32 ls = offs + es;          // tile-local slot in the S stream
+    u32 ll = tots + offl + el;   // tile-local slot in the L stream, staged behind the S members
     u32 curg = s_exg + offg + eg;  // kept L heads up to and including the current slot
+    u32 nrv[RR_IPT];
 #pragma unroll
     for (int q = 0; q < RR_IPT; q++) {
+        nrv[q] = 0;
         if ((u32)q < mine) {
             const u32 j = j0 + q;
             if ((hbits >> q) & 1) curh = j + 1;
             const u32 jh = curh - 1;  // every slot has a head at or before it (slot gst[j] is one)
             const u32 nr = vg[q] + (jh - vs[q]);
-            if (nr_out) nr_out[j] = nr;
-            else if (nr != vg[q]) rank[vi[q]] = nr;
+            nrv[q] = nr;
+            if (!nr_out && nr != vg[q]) rank[vi[q]] = nr;
             if ((kbits >> q) & 1) {
+                u32 slot;
                 if ((sbits >> q) & 1) {
-                    outS.idx[curs] = vi[q];
-                    outS.grp[curs] = nr;
-                    outS.gst[curs] = curs - (j - jh);
-                    curs++;
+                    slot = ls++;
                 } else {
                     curg += (hbits >> q) & 1;
-                    outL.idx[curl] = vi[q];
-                    outL.grp[curl] = nr;
-                    outL.gst[curl] = curl - (j - jh);
-                    outL.gid[curl] = curg - 1;
-                    curl++;
+                    slot = ll++;
+                    st_gid[slot] = curg - 1;
                 }
+                st_idx[slot] = vi[q];
+                st_grp[slot] = nr;
+                st_aux[slot] = j - jh;  // distance to the group head: gst = own position - distance
             }
         }
+    }
+    if (nr_out) {
+        if (full) {
+            ((uint4 *)(nr_out + j0))[0] = make_uint4(nrv[0], nrv[1], nrv[2], nrv[3]);
+            ((uint4 *)(nr_out + j0))[1] = make_uint4(nrv[4], nrv[5], nrv[6], nrv[7]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < RR_IPT; q++)
+                if ((u32)q < mine) nr_out[j0 + q] = nrv[q];
+        }
+    }
+    if (tots + totl == 0) return;  // uniform over the block
+    __syncthreads();
+    const u32 gS0 = (baseS ? *baseS : 0u) + s_exs, gL0 = s_exl;
+    for (u32 t = tid; t < tots; t += RR_NT) {
+        const u32 p = gS0 + t;
+        outS.idx[p] = st_idx[t];
+        outS.grp[p] = st_grp[t];
+        outS.gst[p] = p - st_aux[t];
+    }
+    for (u32 t = tid; t < totl; t += RR_NT) {
+        const u32 p = gL0 + t, u = tots + t;
+        outL.idx[p] = st_idx[u];
+        outL.grp[p] = st_grp[u];
+        outL.gst[p] = p - st_aux[u];
+        outL.gid[p] = st_gid[u];
     }
 }
 
