@@ -289,3 +289,4 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
     }
     OS_PHASE(8);
 }
+
