@@ -82,6 +82,17 @@ typedef std::function<void(const u64 *, const u32 *, u64 *, u32 *, int)> launche
 
 static void run_kernel(const char *name, const void *kern, launcher_t launch, int NT, int IPT, size_t smem_bytes, Bufs &b,
                        u32 m, int reps, int dist);
+
+template <int NT, int IPT, int MINB, int LB>
+static void run_config(const char *name, Bufs &b, u32 m, int reps, int dist)
+{
+    os_kernel_t kern = k_onesweep_pass<u64, NT, IPT, MINB, LB>;
+    const size_t sm = OsSmem<u64, NT, IPT>::bytes;
+    run_kernel(name, (const void *)kern, [=](const u64 *ki, const u32 *vi, u64 *ko, u32 *vo, int p) {
+        kern<<<(m + NT * IPT - 1) / (NT * IPT), NT, sm>>>(ki, vi, ko, vo, m, p * 8, b.hist + p * 256, b.status, g_epoch);
+    }, NT, IPT, sm, b, m, reps, dist);
+}
+
 static void run_kernel(const char *name, const void *kern, launcher_t launch, int NT, int IPT, size_t smem_bytes, Bufs &b,
                        u32 m, int reps, int dist)
 {
