@@ -455,7 +455,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             "transform": {"factors": last_f["factors"], "longest_factor": last_f["longest_factor"],
                           "alphabet_bits": last_f["alphabet_bits"], "initial_depth": last_f["initial_depth"],
                           "doubling_rounds": last_f["rounds"], "radix_passes": last_f["radix_passes"],
-                          "local_sort_rounds": last_f["local_rounds"],
+                          "local_sort_rounds": last_f["local_rounds"], "cta_sort_rounds": last_f["cta_rounds"],
                           "live_sum": last_f["live_sum"], "cycles": last_i["factors"],
                           "splitters": last_i["splitters"], "unreached": last_i["unreached"]},
         }

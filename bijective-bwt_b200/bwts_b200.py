@@ -40,7 +40,7 @@ class Stats(ctypes.Structure):
         ("len", ctypes.c_long), ("direction", ctypes.c_int), ("factors", ctypes.c_long),
         ("longest_factor", ctypes.c_long), ("alphabet_bits", ctypes.c_int), ("initial_depth", ctypes.c_int),
         ("rounds", ctypes.c_int), ("radix_passes", ctypes.c_int), ("local_rounds", ctypes.c_int),
-        ("live_sum", ctypes.c_long),
+        ("cta_rounds", ctypes.c_int), ("live_sum", ctypes.c_long),
         ("splitters", ctypes.c_long), ("unreached", ctypes.c_long), ("launches", ctypes.c_long),
         ("total_ms", ctypes.c_double),
         ("class_launches", ctypes.c_long * NCLASS), ("class_ms", ctypes.c_double * NCLASS),

@@ -41,6 +41,7 @@ static long g_tune_onesweep = 0;   // onesweep tile configuration (see radix_sor
 static long g_tune_local = 0;      // 1 = never use the warp-local sort path
 static long g_tune_lyndon = 0;     // 1 = always take the suffix-sort fallback for the Lyndon boundaries
 static long g_tune_keybits = 0;    // cap on the bits of the initial packed key (0 = 64)
+static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L set
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 
 static bool use_binned_scatter(unsigned n, unsigned kb)
@@ -491,23 +492,50 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             sortedS = true;
         }
         if (mL) {
-            // high part of the key: the dense group index (fewest bits); with routing off the
-            // group start offset does the same job
-            const u32 *hi = groupsL ? gid[g] : gst[g];
-            const int hibits = max(1, bit_length(groupsL ? (u64)groupsL - 1 : (u64)mL - 1));
-            const int passes = max(1, (int)cdiv((u64)kb + hibits, 8));
-            rc = radix_prepare(ctx, st, sb);
-            if (rc) return rc;
-            const u32 bgrid = min(cdiv(mL, 256), 148u * 8u);
-            if (!linear) {
-                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<false>, bgrid, 256, sb.v[sb.cur], hi, mL, rank, FS,
-                       cidx, n, (u32)k, kb, sb.k[sb.cur], passes, sb.hist);
-            } else {
-                LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<true>, bgrid, 256, sb.v[sb.cur], hi, mL, rank, FS,
-                       cidx, n, (u32)k, kb, sb.k[sb.cur], passes, sb.hist);
+            // groups that fit one CTA: gather + bitonic network in shared memory, no radix passes
+            bool cta_sorted = false;
+            if (!g_tune_nocta) {
+                CK(cudaMemsetAsync(small + 5, 0, 4, st));
+                LAUNCH(KC_LOCAL_SORT, 0, k_ls_probe, cdiv(cdiv(mL, LS_T), 256), 256, gst[g], mL, small + 5);
+                rc = readback(ctx, st, small + 5, 4);
+                if (rc) return rc;
+                if (ctx->h_small[0] == 0) {
+                    LaunchRec r__;
+                    r__.cls = KC_LOCAL_SORT; r__.bytes = 32.0 * mL; r__.e0 = r__.e1 = nullptr;
+                    if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
+                    if (!linear)
+                        k_local_sort_cta<false><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
+                            sb.v[sb.cur], gst[g], mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                    else
+                        k_local_sort_cta<true><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
+                            sb.v[sb.cur], gst[g], mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                    if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
+                    ctx->recs.push_back(r__);
+                    CK(cudaGetLastError());
+                    sb.cur ^= 1;
+                    ctx->stats.cta_rounds++;
+                    cta_sorted = true;
+                }
             }
-            rc = radix_sort(ctx, st, sb, mL, passes, false, true);
-            if (rc) return rc;
+            if (!cta_sorted) {
+                // high part of the key: the dense group index (fewest bits); with routing off the
+                // group start offset does the same job
+                const u32 *hi = groupsL ? gid[g] : gst[g];
+                const int hibits = max(1, bit_length(groupsL ? (u64)groupsL - 1 : (u64)mL - 1));
+                const int passes = max(1, (int)cdiv((u64)kb + hibits, 8));
+                rc = radix_prepare(ctx, st, sb);
+                if (rc) return rc;
+                const u32 bgrid = min(cdiv(mL, 256), 148u * 8u);
+                if (!linear) {
+                    LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<false>, bgrid, 256, sb.v[sb.cur], hi, mL, rank, FS,
+                           cidx, n, (u32)k, kb, sb.k[sb.cur], passes, sb.hist);
+                } else {
+                    LAUNCH(KC_BUILD_KEYS, 20.0 * mL, k_build_keys<true>, bgrid, 256, sb.v[sb.cur], hi, mL, rank, FS,
+                           cidx, n, (u32)k, kb, sb.k[sb.cur], passes, sb.hist);
+                }
+                rc = radix_sort(ctx, st, sb, mL, passes, false, true);
+                if (rc) return rc;
+            }
             sortedL = true;
         }
         k *= 2;
@@ -668,6 +696,8 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     OS_ATTR(u64, 1024, 8, 1, 8);
     OS_ATTR(u64, 256, 8, 4, 8);
     OS_ATTR(u32, 384, 8, 3, 8);
+    cudaFuncSetAttribute(k_local_sort_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LS_CAP * sizeof(u64)));
+    cudaFuncSetAttribute(k_local_sort_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LS_CAP * sizeof(u64)));
 #undef OS_ATTR
     bwts_b200_ctx *ctx = new bwts_b200_ctx();
     ctx->device = device;
@@ -1121,5 +1151,6 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 5) { g_tune_pipeline = value; return 0; }
     if (key == 6) { g_tune_keybits = value; return 0; }
     if (key == 7) { g_tune_scatterbin = value; return 0; }
+    if (key == 8) { g_tune_nocta = value; return 0; }
     return BWTS_B200_EINVAL;
 }

@@ -580,6 +580,116 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *__restrict__
         }
 }
 
+// ---- CTA-local sort: one doubling round of a live set whose groups fit one CTA ------------------
+// Same ownership rule as the warp kernel, one level up: CTA c owns the whole groups between the
+// group holding live slot c*LS_T and the group holding slot (c+1)*LS_T.  With every group at most
+// LS_T members that is at most 2*LS_T - 1 slots; they are gathered once, ordered by
+// (group, key2, slot) with a bitonic network in shared memory and written once -- against
+// 6-8 onesweep passes over HBM on the global path (the 4096-copy classes of the tiled C3 input
+// stay at this size for ~19 rounds).
+#define LS_NT 512
+#define LS_T 4096
+#define LS_CAP (2 * LS_T)
+
+// *oversize = 1 if some CTA of k_local_sort_cta would own more than LS_CAP slots
+__global__ void k_ls_probe(const u32 *__restrict__ gst, u32 m, u32 *__restrict__ oversize)
+{
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((u64)c * LS_T >= m) return;
+    const u32 lo = __ldg(gst + c * LS_T);
+    const u32 hi = ((u64)(c + 1) * LS_T < m) ? __ldg(gst + (c + 1) * LS_T) : m;
+    if (hi - lo > LS_CAP) *oversize = 1u;
+}
+
+template <bool LINEAR>
+__global__ void __launch_bounds__(LS_NT, 2) k_local_sort_cta(const u32 *__restrict__ idx, const u32 *__restrict__ gst,
+                                                             u32 m, const u32 *__restrict__ rank,
+                                                             const u32 *__restrict__ FS, const u32 *__restrict__ cidx,
+                                                             u32 k, u32 kb, u32 n, u64 *__restrict__ keys_out,
+                                                             u32 *__restrict__ idx_out)
+{
+    extern __shared__ __align__(16) u64 s_key[];  // LS_CAP words
+    const u32 tid = threadIdx.x;
+    const u32 c = blockIdx.x;
+    const u32 lo = __ldg(gst + c * LS_T);
+    const u32 hi = ((u64)(c + 1) * LS_T < m) ? __ldg(gst + (c + 1) * LS_T) : m;
+    const u32 cnt = hi - lo;
+    if (cnt == 0 || cnt > LS_CAP) return;  // nothing owned / refused by k_ls_probe beforehand
+    u32 P = 64;
+    while (P < cnt) P <<= 1;
+
+    // gather: key = local group start (13 bits) | key2 (31 bits) | slot (13 bits)
+    for (u32 s = tid; s < P; s += LS_NT) {
+        u64 key = ~0ull;
+        if (s < cnt) {
+            const u32 j = lo + s;
+            const u32 i = ldg_stream_u32(idx + j);
+            const u32 g = ldg_stream_u32(gst + j) - lo;
+            u32 r;
+            if (LINEAR) {
+                const u64 t = (u64)i + k;
+                r = (t < n) ? __ldg(rank + (u32)t) + 1 : 0;
+            } else {
+                const u32 f = factor_of(FS, cidx, i);
+                const u32 fs = __ldg(FS + f), len = __ldg(FS + f + 1) - fs;
+                u32 o = i - fs;
+                if (len > 1) {
+                    o += (k < len) ? k : k % len;
+                    if (o >= len) o -= len;
+                }
+                r = __ldg(rank + fs + o);
+            }
+            key = ((u64)g << 44) | ((u64)r << 13) | (u64)s;
+        }
+        s_key[s] = key;
+    }
+    __syncthreads();
+
+    // bitonic network; strides below 8 run in registers on 8 consecutive words per thread
+    for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
+        u32 j = k2 >> 1;
+        for (; j >= 8; j >>= 1) {
+            for (u32 t = tid; t < P / 2; t += LS_NT) {
+                const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const u32 l = i + j;
+                const bool up = (i & k2) == 0;
+                const u64 a = s_key[i], b = s_key[l];
+                if ((a > b) == up) { s_key[i] = b; s_key[l] = a; }
+            }
+            __syncthreads();
+        }
+        for (u32 base = tid * 8; base < P; base += LS_NT * 8) {
+            u64 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = s_key[base + q];
+            const bool up = (base & k2) == 0;  // k2 >= 8 here or the whole 8-block shares the direction bits below
+#pragma unroll
+            for (int jj = 4; jj > 0; jj >>= 1) {
+                if ((u32)jj > j) continue;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (q & jj) continue;
+                    const bool upq = (k2 >= 8) ? up : (((base + q) & k2) == 0);
+                    const u64 a = v[q], b = v[q + jj];
+                    if ((a > b) == upq) { v[q] = b; v[q + jj] = a; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) s_key[base + q] = v[q];
+        }
+        __syncthreads();
+    }
+
+    for (u32 s = tid; s < cnt; s += LS_NT) {
+        const u64 key = s_key[s];
+        const u32 src = (u32)key & (LS_CAP - 1);
+        const u32 r = (u32)(key >> 13) & 0x7fffffffu;
+        const u32 g = (u32)(key >> 44);
+        keys_out[lo + s] = ((u64)(lo + g) << kb) | (u64)r;
+        idx_out[lo + s] = __ldg(idx + lo + src);
+    }
+}
+
 // ---- emit -----------------------------------------------------------------------------------------
 // out[rank[i]] = T[i-1] for every position that does not start a factor and whose rank lies in
 // [lo, hi).  Large outputs are emitted in rank windows small enough to stay in L2, so the

@@ -99,6 +99,7 @@ typedef struct {
     int    rounds;              /* forward: doubling rounds after the initial sort      */
     int    radix_passes;        /* forward: onesweep passes launched                    */
     int    local_rounds;        /* forward: rounds served by the warp-local sort        */
+    int    cta_rounds;          /* forward: rounds whose large-group set was sorted CTA-locally */
     long   live_sum;            /* forward: sum over rounds of live elements            */
     long   splitters;           /* inverse: sublists                                    */
     long   unreached;           /* inverse: elements ranked by the self-walk fallback   */
@@ -129,7 +130,8 @@ const char *bwts_b200_version(void);
  * warp-local sort path (1), 4 = force the suffix-sort fallback for the Lyndon boundaries (1),
  * 5 = no copy/compute overlap between the blocks of one device (1), 6 = cap on the bits of
  * the initial packed key (8..64), 7 = binned rank scatter of the first re-rank (1 = never,
- * 2 = always; default: inputs of 4 Mi bytes and more).  value 0 = default.               */
+ * 2 = always; default: inputs of 4 Mi bytes and more), 8 = never sort the large-group set
+ * CTA-locally (1).  value 0 = default.                                                  */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

@@ -173,6 +173,33 @@ def test_binned_rank_scatter_forced_on_small_inputs(bwts, ctx, oracle, gen):
         bwts.tune(7, 0)
 
 
+def test_cta_local_sort_path_and_radix_path_agree(bwts, ctx, oracle, gen):
+    """rounds whose large-group set fits the CTA-local bitonic sort (default) and the global radix
+    path for them (tune 8 = 1) must both equal the oracle; with the warp-local path off (tune 3)
+    every live group goes through the CTA-local sort"""
+    fam = helpers.families(300_000)
+    cases = [gen.make("tiled", 80, 2_500_000), gen.make("dna", 81, 1_500_000), gen.make("text", 82, 1_000_000),
+             fam["ww"], fam["runs"], fam["thue_morse"], fam["de_bruijn"], fam["random2"], helpers.fibonacci_word(200_000)]
+    used = 0
+    for x in cases:
+        want = oracle.forward(x)
+        for local_off in (0, 1):
+            bwts.tune(3, local_off)
+            bwts.tune(8, 0)
+            a = ctx.forward_host(x)
+            used += ctx.stats()["cta_rounds"]
+            bwts.tune(8, 1)
+            b = ctx.forward_host(x)
+            assert ctx.stats()["cta_rounds"] == 0
+            bwts.tune(8, 0)
+            bwts.tune(3, 0)
+            assert a == want and b == want
+    assert used > 0, "the CTA-local sort never ran"
+    # suffix-array mode (linear successor) through the same kernel
+    y = gen.make("tiled", 83, 700_000)
+    assert np.array_equal(bwts.suffix_array(y), oracle.suffix_array(y))
+
+
 def test_block_pipeline_many_ragged_blocks(bwts, oracle, gen):
     """per device: loader / compute / drainer overlap over many blocks; pageable buffers
     go through the pinned chunk rings (blocks larger than one 8 MiB chunk and much smaller ones)"""
