@@ -60,7 +60,7 @@ def lib():
     if not LIB_PATH.exists():
         raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
                           "(nvcc, sm_100a). There is no CPU fallback.")
-    L = ctypes.CDLL(str(LIB_PATH))
+    L = ctypes.CDLL(os.environ.get("BWTS_B200_LIB", str(LIB_PATH)))  # override: diagnostic builds (make profile-lib)
     vp, cl, ci = ctypes.c_void_p, ctypes.c_long, ctypes.c_int
     for name in ("bwts_b200_forward", "bwts_b200_inverse"):
         getattr(L, name).argtypes = [vp, cl, vp, ci]

@@ -1141,6 +1141,18 @@ extern "C" const char *bwts_b200_strerror(int code)
 }
 extern "C" int bwts_b200_last_cuda_error(const bwts_b200_ctx *ctx) { return ctx ? ctx->last_cuda : 0; }
 extern "C" const char *bwts_b200_version(void) { return BWTS_VERSION; }
+#ifdef BWTS_PROFILE_PHASES
+// diagnostic builds only (make profile-lib): per-phase cycle sums of the instrumented kernels
+extern "C" int bwts_b200_debug_phases(unsigned long long *out32, int reset)
+{
+    if (out32 && cudaMemcpyFromSymbol(out32, g_phase, 32 * sizeof(unsigned long long)) != cudaSuccess) return BWTS_B200_ECUDA;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(g_phase, z, sizeof z) != cudaSuccess) return BWTS_B200_ECUDA;
+    }
+    return 0;
+}
+#endif
 extern "C" int bwts_b200_tune(int key, long value)
 {
     if (key == 0) { if (value < 0) return BWTS_B200_EINVAL; g_tune_chunk = value; return 0; }

@@ -10,6 +10,28 @@ typedef uint64_t u64;
 typedef int32_t  i32;
 
 #define FULL_MASK 0xffffffffu
+
+// Per-phase cycle counters (diagnostic builds only: -DBWTS_PROFILE_PHASES, `make profile-lib`, or
+// OS_PROFILE_PHASES in tests/bench_onesweep.cu).  Thread 0 of every CTA adds the cycles since
+// its previous mark to g_phase[slot]; slots 0-8 onesweep, 16-27 re-rank.
+#if defined(OS_PROFILE_PHASES) && !defined(BWTS_PROFILE_PHASES)
+#define BWTS_PROFILE_PHASES
+#endif
+#ifdef BWTS_PROFILE_PHASES
+__device__ unsigned long long g_phase[32];
+#define PH_INIT() long long ph_t_prev__ = clock64()
+#define PH(i_)                                                                \
+    do {                                                                      \
+        if (threadIdx.x == 0) {                                               \
+            const long long t__ = clock64();                                  \
+            atomicAdd(&g_phase[i_], (unsigned long long)(t__ - ph_t_prev__)); \
+            ph_t_prev__ = t__;                                                \
+        }                                                                     \
+    } while (0)
+#else
+#define PH_INIT() do { } while (0)
+#define PH(i_) do { } while (0)
+#endif
 #define NONE32 0xffffffffu
 
 static __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
     __shared__ u32 s_exh, s_exs, s_exl, s_exg;
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    PH_INIT();
     if (tid < 8) s_hb[RR_NT + tid] = 0;
     __syncthreads();
     // tile = blockIdx.x: CTAs are dispatched in index order, so the tiles a look-back waits for
@@ -291,7 +292,9 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
     if (mine < RR_IPT) hbits |= 1u << mine;  // the slot after the last live slot acts as a head
     s_hb[tid] = (u8)hbits;
     if (tid == RR_NT - 1) s_hb[RR_NT] = (u8)(hbits >> RR_IPT);
+    PH(16);  // loads + head flags
     __syncthreads();
+    PH(17);
 
     // ---- per slot: keep?  which stream?
     // next head strictly after tile slot hs, looked for in the following 32 slots
@@ -347,6 +350,7 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
         }
     }
 
+    PH(18);  // keep / route
     // ---- block-wide scans of (max lasth, sum nS, sum nL)
     const u32 ih = warp_incl_max(lasth), is = warp_incl_sum(nS), il = warp_incl_sum(nL), ig = warp_incl_sum(nG);
     if (lane == 31) { s_wh[warp] = ih; s_ws[warp] = is; s_wl[warp] = il; s_wg[warp] = ig; }
@@ -370,6 +374,7 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
         totg += s_wg[w];
     }
 
+    PH(19);  // scans
     // ---- decoupled look-back on (max, sum, sum), by warp 0
     if (warp == 0) {
         u32 exh = 0, exs = 0, exl = 0, exg = 0;
@@ -424,7 +429,9 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
             }
         }
     }
+    PH(20);  // look-back (thread 0 is in warp 0)
     __syncthreads();
+    PH(21);
 
     // ---- outputs.  Ranks: 8 consecutive slots per thread (vector store) or a scatter of the
     // changed ones.  Compaction: through shared memory, S members packed from slot 0, L members
@@ -476,8 +483,10 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
                 if ((u32)q < mine) nr_out[j0 + q] = nrv[q];
         }
     }
+    PH(22);  // ranks + staging
     if (tots + totl == 0) return;  // uniform over the block
     __syncthreads();
+    PH(23);
     const u32 gS0 = (baseS ? *baseS : 0u) + s_exs, gL0 = s_exl;
     for (u32 t = tid; t < tots; t += RR_NT) {
         const u32 p = gS0 + t;
@@ -492,6 +501,7 @@ __global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, 
         outL.gst[p] = p - st_aux[u];
         outL.gid[p] = st_gid[u];
     }
+    PH(24);  // coalesced stream writes
 }
 
 // ---- local sort: one doubling round when every live group has at most 32 members ---------------

@@ -22,22 +22,8 @@
 #define OS_FLAG_AGG 1ull
 #define OS_FLAG_PREFIX 2ull
 
-// per-phase cycle counters of the onesweep kernel: only tests/bench_onesweep.cu defines this
-#ifdef OS_PROFILE_PHASES
-__device__ unsigned long long g_os_phase[16];
-#define OS_PHASE_INIT() long long os_t_prev__ = clock64()
-#define OS_PHASE(i_)                                                            \
-    do {                                                                        \
-        if (threadIdx.x == 0) {                                                 \
-            const long long t__ = clock64();                                    \
-            atomicAdd(&g_os_phase[i_], (unsigned long long)(t__ - os_t_prev__)); \
-            os_t_prev__ = t__;                                                  \
-        }                                                                       \
-    } while (0)
-#else
-#define OS_PHASE_INIT() do { } while (0)
-#define OS_PHASE(i_) do { } while (0)
-#endif
+#define OS_PHASE_INIT() PH_INIT()
+#define OS_PHASE(i_) PH(i_)
 
 static __device__ __forceinline__ u64 os_pack(u32 epoch, u64 flag, u32 value)
 {
@@ -166,8 +152,8 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
         const u32 g = wbase + j * 32 + lane;
         val[j] = (g < m) ? (vin ? ldg_stream_u32(vin + g) : g) : 0u;
     }
-#ifdef OS_PROFILE_PHASES
-    if (key[IPT - 1] == (K)0x123456789abcdefull && val[IPT - 1] == 0x1234567u) g_os_phase[15] = 1;  // wait for the loads
+#ifdef BWTS_PROFILE_PHASES
+    if (key[IPT - 1] == (K)0x123456789abcdefull && val[IPT - 1] == 0x1234567u) g_phase[15] = 1;  // wait for the loads
 #endif
     OS_PHASE(1);
 

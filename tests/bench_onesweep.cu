@@ -112,8 +112,8 @@ static void run_kernel(const char *name, const void *kern, launcher_t launch, in
     for (int p = 0; p < passes; p++) { best[p] = 1e9; sum[p] = 0; }
     u32 errors = 0;
 #ifdef OS_PROFILE_PHASES
-    unsigned long long zero[16] = {0};
-    CHECK(cudaMemcpyToSymbol(g_os_phase, zero, sizeof zero));
+    unsigned long long zero[32] = {0};
+    CHECK(cudaMemcpyToSymbol(g_phase, zero, sizeof zero));
 #endif
     for (int r = 0; r < reps + 1; r++) {
         CHECK(cudaMemcpy(b.k[0], b.orig, (size_t)m * 8, cudaMemcpyDeviceToDevice));
@@ -146,8 +146,8 @@ static void run_kernel(const char *name, const void *kern, launcher_t launch, in
     printf(" | avg %.0f GB/s (%.1f%% of 6552.6) best-pass %.0f GB/s | %s\n", totb / (tot * 1e-3) / 1e9,
            100.0 * totb / (tot * 1e-3) / 1e9 / 6552.6, 24.0 * m / (best[1] * 1e-3) / 1e9, errors ? "WRONG" : "ok");
 #ifdef OS_PROFILE_PHASES
-    unsigned long long ph[16];
-    CHECK(cudaMemcpyFromSymbol(ph, g_os_phase, sizeof ph));
+    unsigned long long ph[32];
+    CHECK(cudaMemcpyFromSymbol(ph, g_phase, sizeof ph));
     const double tiles = (double)((m + NT * IPT - 1) / (NT * IPT)) * passes * (reps + 1);
     static const char *pn[9] = {"ticket+zero", "loads", "rank", "sync(rank)", "digit-scan", "stage", "look-back",
                                 "sync(lb)", "write"};
