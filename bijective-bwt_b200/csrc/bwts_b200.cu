@@ -41,6 +41,7 @@ static long g_tune_onesweep = 0;   // onesweep tile configuration (see radix_sor
 static long g_tune_local = 0;      // 1 = never use the warp-local sort path
 static long g_tune_lyndon = 0;     // 1 = always take the suffix-sort fallback for the Lyndon boundaries
 static long g_tune_keybits = 0;    // cap on the bits of the initial packed key (0 = 64)
+static long g_tune_emit = 0;       // emit: 0 = binned from 512 Mi bytes, 1 = always rank windows, 2 = always binned
 static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L set
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 
@@ -543,12 +544,32 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
 
     // -- emit
     if (!linear) {
-        // rank windows of 64 Mi slots: the scatter target of one launch stays resident in the 126 MB L2
-        const u32 win = 64u << 20;
-        for (u64 lo = 0; lo < n; lo += win) {
-            const u32 hi = (u32)min((u64)n, lo + win);
-            LAUNCH(KC_EMIT, (lo == 0 ? 7.0 : 4.0) * n, k_emit, cdiv(cdiv(n, 4), 256), 256, dT, n, rank, flags, d_out,
-                   (u32)lo, hi);
+        const bool emit_binned = g_tune_emit == 2 || (g_tune_emit == 0 && n >= (512u << 20));
+        if (emit_binned && kb >= 8) {
+            // (rank, byte) pairs binned by rank region, then scattered through L2; the sort buffers are idle
+            u32 *val = (u32 *)sb.k[0], *bin_pos = val + (((size_t)n + 3) & ~(size_t)3);
+            u32 *bin_val = (u32 *)sb.k[1];
+            const u32 shift = kb - 8;
+            LAUNCH(KC_EMIT, 5.0 * n, k_emit_vals, cdiv(cdiv(n, 4), 256), 256, dT, n, val);
+            LAUNCH(KC_EMIT, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
+            do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
+            LaunchRec r__;
+            r__.cls = KC_EMIT; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr;
+            if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
+            k_onesweep_pass<u32, 384, 8, 3, 8><<<cdiv(n, 384 * 8), 384, OsSmem<u32, 384, 8>::bytes, st>>>(
+                rank, val, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
+            if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
+            ctx->recs.push_back(r__);
+            CK(cudaGetLastError());
+            LAUNCH(KC_EMIT, 9.0 * n, k_scatter_bytes, cdiv(cdiv(n, 4), 256), 256, bin_pos, bin_val, n, d_out);
+        } else {
+            // rank windows of 64 Mi slots: the scatter target of one launch stays resident in the 126 MB L2
+            const u32 win = 64u << 20;
+            for (u64 lo = 0; lo < n; lo += win) {
+                const u32 hi = (u32)min((u64)n, lo + win);
+                LAUNCH(KC_EMIT, (lo == 0 ? 7.0 : 4.0) * n, k_emit, cdiv(cdiv(n, 4), 256), 256, dT, n, rank, flags, d_out,
+                       (u32)lo, hi);
+            }
         }
         LAUNCH(KC_EMIT, 10.0 * F, k_emit_heads, cdiv(F, 256), 256, dT, FS, F, rank, d_out);
     } else if (mode == FWD_SA) {
@@ -1164,5 +1185,6 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 6) { g_tune_keybits = value; return 0; }
     if (key == 7) { g_tune_scatterbin = value; return 0; }
     if (key == 8) { g_tune_nocta = value; return 0; }
+    if (key == 9) { g_tune_emit = value; return 0; }
     return BWTS_B200_EINVAL;
 }

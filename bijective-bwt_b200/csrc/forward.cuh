@@ -722,6 +722,32 @@ __global__ void __launch_bounds__(256) k_emit(const u8 *__restrict__ T, u32 n, c
         }
     }
 }
+// Binned emit for outputs far larger than L2 (the windowed form above re-reads rank[] once per
+// 64 Mi-slot window: 16 sweeps at 1 GiB).  val[i] = T[i-1] widened to 32 bits; one u32 onesweep
+// pass bins the (rank[i], val[i]) pairs by the top 8 bits of the rank -- after the final re-rank
+// the ranks are a permutation of 0..n-1, so the bin starts are known (k_bin_bases) -- and
+// k_scatter_bytes writes them region by region.  Factor heads are overwritten afterwards.
+__global__ void __launch_bounds__(256) k_emit_vals(const u8 *__restrict__ T, u32 n, u32 *__restrict__ val)
+{
+    const u32 i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (i0 + q < n) val[i0 + q] = (i0 + q > 0) ? (u32)T[i0 + q - 1] : 0u;
+}
+__global__ void __launch_bounds__(256) k_scatter_bytes(const u32 *__restrict__ pos, const u32 *__restrict__ val, u32 n,
+                                                       u8 *__restrict__ out)
+{
+    const u32 j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= n) return;
+    if (j0 + 4 <= n) {
+        const uint4 p = ldg_stream_u4((const uint4 *)(pos + j0));
+        const uint4 v = ldg_stream_u4((const uint4 *)(val + j0));
+        out[p.x] = (u8)v.x; out[p.y] = (u8)v.y; out[p.z] = (u8)v.z; out[p.w] = (u8)v.w;
+    } else {
+        for (u32 j = j0; j < n; j++) out[pos[j]] = (u8)val[j];
+    }
+}
 // factor heads receive the last byte of their own factor
 __global__ void __launch_bounds__(256) k_emit_heads(const u8 *__restrict__ T, const u32 *__restrict__ FS, u32 F,
                                                     const u32 *__restrict__ rank, u8 *__restrict__ out)

@@ -131,7 +131,8 @@ const char *bwts_b200_version(void);
  * 5 = no copy/compute overlap between the blocks of one device (1), 6 = cap on the bits of
  * the initial packed key (8..64), 7 = binned rank scatter of the first re-rank (1 = never,
  * 2 = always; default: inputs of 4 Mi bytes and more), 8 = never sort the large-group set
- * CTA-locally (1).  value 0 = default.                                                  */
+ * CTA-locally (1), 9 = emit through rank windows (1) or binned by rank region (2; default:
+ * binned from 512 Mi bytes).  value 0 = default.                                        */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

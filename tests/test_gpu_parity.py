@@ -200,6 +200,20 @@ def test_cta_local_sort_path_and_radix_path_agree(bwts, ctx, oracle, gen):
     assert np.array_equal(bwts.suffix_array(y), oracle.suffix_array(y))
 
 
+def test_binned_emit_forced_on_small_inputs(bwts, ctx, oracle, gen):
+    """emit as (rank, byte) pairs binned by rank region (default from 512 Mi bytes), forced here"""
+    bwts.tune(9, 2)
+    try:
+        for n in (256, 257, 1000, 3073, 70_001):
+            for name, x in helpers.families(n).items():
+                assert ctx.forward_host(x) == oracle.forward(x), (name, n)
+        for kind, seed, n in (("text", 27, 3_000_001), ("dna", 28, 2_000_003), ("tiled", 29, 1_500_000)):
+            x = gen.make(kind, seed, n)
+            assert ctx.forward_host(x) == oracle.forward(x), kind
+    finally:
+        bwts.tune(9, 0)
+
+
 def test_block_pipeline_many_ragged_blocks(bwts, oracle, gen):
     """per device: loader / compute / drainer overlap over many blocks; pageable buffers
     go through the pinned chunk rings (blocks larger than one 8 MiB chunk and much smaller ones)"""
