@@ -674,10 +674,9 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     }
 
     // -- offsets of the cycles, in order of ascending smallest index
-    LAUNCH(KC_INV_SCAN, 4.0 * n, k_tile_sum_u32, nsc, 256, len_at_min, n, tilecnt);
+    LAUNCH(KC_INV_SCAN, 4.0 * n, k_tile_sum_u32, nsc, 256, len_at_min, n, tilecnt, small + 6);  // also counts the cycles
     LAUNCH(KC_INV_SCAN, 8.0 * nsc, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, nsc, small + 8);
     LAUNCH(KC_INV_SCAN, 8.0 * n, k_tile_scan_apply_u32, nsc, 256, len_at_min, off, n, tilecnt);
-    LAUNCH(KC_INV_SCAN, 4.0 * n, k_inv_count_cycles, min(cdiv(n, 256), 148u * 8u), 256, len_at_min, n, small + 6);
 
     // -- placement: second walk writes the bytes at descending consecutive positions
     LAUNCH(KC_INV_PLACE, 44.0 * ns, k_inv_spl_record, gs, 256, jmR, pv[pc], cyc, off, ns, srec);

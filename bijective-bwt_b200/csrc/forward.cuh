@@ -215,7 +215,7 @@ struct LiveOut {  // one compaction stream
 // rank[idx[j]]; the caller bins the (idx, rank) pairs by text region and scatters them with
 // locality (first re-rank of large inputs, where every one of the n ranks is written).
 template <bool ROUTE>
-__global__ void __launch_bounds__(RR_NT) k_rerank(const u64 *__restrict__ keys, const u32 *__restrict__ idx,
+__global__ void __launch_bounds__(RR_NT, 4) k_rerank(const u64 *__restrict__ keys, const u32 *__restrict__ idx,
                                                   const u32 *__restrict__ grp, const u32 *__restrict__ gst, u32 m,
                                                   int finalize, u32 *__restrict__ rank, LiveOut outS,
                                                   const u32 *__restrict__ baseS, LiveOut outL,

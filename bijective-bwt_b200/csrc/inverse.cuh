@@ -384,11 +384,3 @@ __global__ void __launch_bounds__(256) k_inv_spl_record(const u64 *__restrict__ 
     srec[s] = make_uint4(A, L, off[cm], 0u);
 }
 
-// count cycles: entries of len_at_min that are non-zero
-__global__ void __launch_bounds__(256) k_inv_count_cycles(const u32 *__restrict__ len_at_min, u32 n, u32 *__restrict__ counter)
-{
-    u32 c = 0;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += len_at_min[i] != 0;
-    c = warp_sum(c);
-    if (lane_id() == 0 && c) atomicAdd(counter, c);
-}

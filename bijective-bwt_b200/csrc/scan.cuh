@@ -39,23 +39,31 @@ __global__ void __launch_bounds__(1024) k_scan_excl_u32_block(const u32 *in, u32
 
 // ---- large arrays: tile sums -> (block scan of the sums) -> apply -------------------------
 #define SC_TILE 4096  // 256 threads x 16 values
-__global__ void __launch_bounds__(256) k_tile_sum_u32(const u32 *__restrict__ in, u32 n, u32 *__restrict__ tile_sum)
+// nonzero != nullptr: the number of non-zero inputs is added to *nonzero (one atomic per tile)
+__global__ void __launch_bounds__(256) k_tile_sum_u32(const u32 *__restrict__ in, u32 n, u32 *__restrict__ tile_sum,
+                                                      u32 *__restrict__ nonzero)
 {
-    __shared__ u32 ws[8];
+    __shared__ u32 ws[8], wz[8];
     const u32 base = blockIdx.x * SC_TILE;
-    u32 s = 0;
+    u32 s = 0, z = 0;
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         const u32 i = base + q * 256 + threadIdx.x;
-        if (i < n) s += ldg_stream_u32(in + i);
+        if (i < n) {
+            const u32 v = ldg_stream_u32(in + i);
+            s += v;
+            z += v != 0;
+        }
     }
     s = warp_sum(s);
-    if (lane_id() == 0) ws[threadIdx.x >> 5] = s;
+    z = warp_sum(z);
+    if (lane_id() == 0) { ws[threadIdx.x >> 5] = s; wz[threadIdx.x >> 5] = z; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        u32 t = 0;
-        for (int w = 0; w < 8; w++) t += ws[w];
+        u32 t = 0, tz = 0;
+        for (int w = 0; w < 8; w++) { t += ws[w]; tz += wz[w]; }
         tile_sum[blockIdx.x] = t;
+        if (nonzero && tz) atomicAdd(nonzero, tz);
     }
 }
 
