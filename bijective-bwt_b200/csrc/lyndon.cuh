@@ -93,9 +93,13 @@ __global__ void __launch_bounds__(128) k_duval_chunks(const u8 *__restrict__ T, 
             if (k >= e && f + (k - i) >= e) { settled = true; break; }
             const u8 ci = T[i], ck = T[k];
             if (ci > ck) break;
-            if (ci < ck) { i = f; k++; continue; }
-            i++; k++;
-            // inside a periodic stretch: skip 8 bytes at a time (i < k)
+            // one select instead of a branch per outcome: the 32 lanes of a warp run 32 different
+            // Duval scans, every extra branch here is executed by the whole warp
+            const bool eq = ci == ck;
+            i = eq ? i + 1 : f;
+            k++;
+            if (!eq || i - f < 16) continue;
+            // 16 bytes into a repetition: skip 8 bytes at a time (i < k)
             while ((u64)k + 16 <= n && load8_unaligned(T + i) == load8_unaligned(T + k)) {
                 i += 8; k += 8;
                 if (k >= e && ((++spent) & 1023) == 0) {
