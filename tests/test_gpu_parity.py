@@ -135,6 +135,24 @@ def test_full_size_properties_64mib(ctx, gen):
     assert ctx.forward_host(ctx.inverse_host(x)) == x
 
 
+@pytest.mark.parametrize("kind,seed,n", [("tiled", 3, 256 << 20), ("dna", 4, 1 << 30)])
+def test_full_size_properties_c3_c4(bwts, gen, kind, seed, n):
+    """BASELINE configs[2] and configs[3] at full size (256 MiB tiled text, 1 GiB DNA):
+    round trip, out[0] == x[-1], byte histogram; 1 GiB also runs the binned emit"""
+    x = gen.make(kind, seed, n)
+    xa = np.frombuffer(x, np.uint8)
+    with bwts.Context(0) as c:
+        y = c.forward_host(x)
+        st = c.stats()
+        assert len(y) == n and y[0] == x[-1]
+        ya = np.frombuffer(y, np.uint8)
+        assert np.array_equal(np.bincount(xa, minlength=256), np.bincount(ya, minlength=256))
+        assert st["rounds"] >= 5 and st["factors"] >= 1
+        back = c.inverse_host(y)
+        assert np.array_equal(np.frombuffer(back, np.uint8), xa)
+        del back, y
+
+
 def test_oracle_sample_16mib(ctx, oracle, gen):
     x = gen.make("text", 2, 16 << 20)
     assert ctx.forward_host(x) == oracle.forward(x)
