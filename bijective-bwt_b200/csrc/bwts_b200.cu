@@ -423,7 +423,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
             ctx->recs.push_back(r__);
             CK(cudaGetLastError());
-            LAUNCH(KC_RERANK, 12.0 * n, k_scatter_pairs, cdiv(cdiv(n, 4), 256), 256, bin_pos, bin_val, n, rank);
+            LAUNCH(KC_RERANK, 12.0 * n, k_scatter_pairs, cdiv(cdiv(n, 8), 256), 256, bin_pos, bin_val, n, rank);
         }
         rc = readback(ctx, st, rrc, 2 * sizeof(RerankCounters));
         if (rc) return rc;

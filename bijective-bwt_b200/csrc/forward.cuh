@@ -709,14 +709,23 @@ __global__ void __launch_bounds__(256) k_emit(const u8 *__restrict__ T, u32 n, c
 {
     const u32 i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i0 >= n) return;
-    if (i0 + 4 <= n) {
+    if (i0 + 4 <= n && i0 >= 4) {
+        // every load is issued before the first store: the ranks, the four flags as one word, and
+        // T[i0-1 .. i0+2] out of the aligned words around it (a word that holds a valid byte lies
+        // inside the allocation)
         const uint4 r = ldg_stream_u4((const uint4 *)(rank + i0));
+        const u32 fl = *(const u32 *)(flags + i0);
+        const uintptr_t a = (uintptr_t)(T + i0 - 1);
+        const u32 *w = (const u32 *)(a & ~(uintptr_t)3);
+        const u32 o = (u32)(a & 3);
+        const u32 w0 = w[0], w1 = o ? w[1] : 0u;
+        const u32 bytes = (u32)((((u64)w1 << 32) | w0) >> (8 * o));
         const u32 rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            if (rr[q] >= lo && rr[q] < hi && !flags[i0 + q]) out[rr[q]] = T[i0 + q - 1];
+            if (rr[q] >= lo && rr[q] < hi && !((fl >> (8 * q)) & 0xffu)) out[rr[q]] = (u8)(bytes >> (8 * q));
     } else {
-        for (u32 i = i0; i < n; i++) {
+        for (u32 i = i0; i < min(n, i0 + 4); i++) {
             const u32 r = rank[i];
             if (r >= lo && r < hi && !flags[i]) out[r] = T[i - 1];
         }
@@ -776,12 +785,14 @@ __global__ void k_bin_bases(u32 n, u32 shift, u32 *__restrict__ base)
 __global__ void __launch_bounds__(256) k_scatter_pairs(const u32 *__restrict__ pos, const u32 *__restrict__ val, u32 n,
                                                        u32 *__restrict__ rank)
 {
-    const u32 j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    // 8 pairs per thread, all four vector loads in flight before the first store
+    const u32 j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (j0 >= n) return;
-    if (j0 + 4 <= n) {
-        const uint4 p = ldg_stream_u4((const uint4 *)(pos + j0));
-        const uint4 v = ldg_stream_u4((const uint4 *)(val + j0));
-        rank[p.x] = v.x; rank[p.y] = v.y; rank[p.z] = v.z; rank[p.w] = v.w;
+    if (j0 + 8 <= n) {
+        const uint4 p0 = ldg_stream_u4((const uint4 *)(pos + j0)), p1 = ldg_stream_u4((const uint4 *)(pos + j0) + 1);
+        const uint4 v0 = ldg_stream_u4((const uint4 *)(val + j0)), v1 = ldg_stream_u4((const uint4 *)(val + j0) + 1);
+        rank[p0.x] = v0.x; rank[p0.y] = v0.y; rank[p0.z] = v0.z; rank[p0.w] = v0.w;
+        rank[p1.x] = v1.x; rank[p1.y] = v1.y; rank[p1.z] = v1.z; rank[p1.w] = v1.w;
     } else {
         for (u32 j = j0; j < n; j++) rank[pos[j]] = val[j];
     }
