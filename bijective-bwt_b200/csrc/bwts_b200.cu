@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -977,6 +978,9 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
         return rc;
     }
 
+    const bool dbg = getenv("BWTS_B200_PIPE_DEBUG") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     const bool in_pinned = host_ptr_is_pinned(in), out_pinned = host_ptr_is_pinned(out);
     const size_t slot_bytes = ((size_t)block_len + 255) & ~(size_t)255;
     u8 *d_io = nullptr;
@@ -995,6 +999,7 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
         rc = BWTS_B200_ECUDA;
     if (rc == 0 && !in_pinned) rc = ring_in.init();
     if (rc == 0 && !out_pinned) rc = ring_out.init();
+    if (dbg) fprintf(stderr, "[pipe dev %d] setup %.2f ms (pinned in/out %d/%d, %zu blocks)\n", dev, since(), (int)in_pinned, (int)out_pinned, mine.size());
     if (rc == 0) {
         u8 *d_in[2] = {d_io, d_io + slot_bytes}, *d_out[2] = {d_io + 2 * slot_bytes, d_io + 3 * slot_bytes};
         Sema in_free(2), in_ready(0), out_free(2), out_ready(0);
@@ -1035,7 +1040,9 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
                 const long b = mine[i];
                 int r = 0;
                 if (cudaStreamWaitEvent(st, ev_loaded[i & 1], 0) != cudaSuccess) r = BWTS_B200_ECUDA;
+                const double t0 = since();
                 if (r == 0) r = run_device(ctx, direction, d_in[i & 1], blk_len(b), d_out[i & 1], nullptr);
+                if (dbg) fprintf(stderr, "[pipe dev %d] block %zu: waited until %.2f, transform %.2f ms (device %.2f)\n", dev, i, t0, since() - t0, ctx->stats.total_ms);
                 if (r) fail(r);
             }
             in_free.release();
@@ -1045,6 +1052,7 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
         drainer.join();
         rc = status.load();
     }
+    if (dbg) fprintf(stderr, "[pipe dev %d] pipeline done at %.2f ms\n", dev, since());
     cudaDeviceSynchronize();
     ring_in.destroy();
     ring_out.destroy();
@@ -1053,6 +1061,7 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
     if (s_in) cudaStreamDestroy(s_in);
     if (s_out) cudaStreamDestroy(s_out);
     if (d_io) cudaFree(d_io);
+    if (dbg) fprintf(stderr, "[pipe dev %d] teardown done at %.2f ms\n", dev, since());
     return rc;
 }
 
