@@ -224,10 +224,10 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
         CK(cudaGetLastError());                                                                           \
     } while (0)
         switch (g_tune_onesweep) {
-        case 1: OS_LAUNCH(512, 8, 2, 8); break;
-        case 2: OS_LAUNCH(1024, 8, 1, 8); break;
-        case 3: OS_LAUNCH(256, 8, 4, 8); break;
-        default: OS_LAUNCH(384, 8, 3, 8); break;
+        case 1: OS_LAUNCH(512, 8, 3, 8); break;
+        case 2: OS_LAUNCH(256, 16, 3, 8); break;
+        case 3: OS_LAUNCH(384, 12, 3, 8); break;
+        default: OS_LAUNCH(384, 12, 3, 4); break;
         }
 #undef OS_LAUNCH
         sb.cur = b;
@@ -419,7 +419,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             LaunchRec r__;
             r__.cls = KC_RERANK; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr;
             if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
-            k_onesweep_pass<u32, 384, 8, 3, 8><<<cdiv(n, 384 * 8), 384, OsSmem<u32, 384, 8>::bytes, st>>>(
+            k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(n, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
                 sb.v[sb.cur], nr_buf, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
             if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
             ctx->recs.push_back(r__);
@@ -557,7 +557,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             LaunchRec r__;
             r__.cls = KC_EMIT; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr;
             if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
-            k_onesweep_pass<u32, 384, 8, 3, 8><<<cdiv(n, 384 * 8), 384, OsSmem<u32, 384, 8>::bytes, st>>>(
+            k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(n, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
                 rank, val, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
             if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
             ctx->recs.push_back(r__);
@@ -712,11 +712,11 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     cudaFuncSetAttribute(k_onesweep_pass<K_, NT_, IPT_, MINB_, LB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                          (int)OsSmem<K_, NT_, IPT_>::bytes);                                                         \
     cudaFuncSetAttribute(k_onesweep_pass<K_, NT_, IPT_, MINB_, LB_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-    OS_ATTR(u64, 384, 8, 3, 8);
-    OS_ATTR(u64, 512, 8, 2, 8);
-    OS_ATTR(u64, 1024, 8, 1, 8);
-    OS_ATTR(u64, 256, 8, 4, 8);
-    OS_ATTR(u32, 384, 8, 3, 8);
+    OS_ATTR(u64, 384, 12, 3, 4);
+    OS_ATTR(u64, 384, 12, 3, 8);
+    OS_ATTR(u64, 512, 8, 3, 8);
+    OS_ATTR(u64, 256, 16, 3, 8);
+    OS_ATTR(u32, 384, 12, 3, 4);
     cudaFuncSetAttribute(k_local_sort_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LS_CAP * sizeof(u64)));
     cudaFuncSetAttribute(k_local_sort_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LS_CAP * sizeof(u64)));
 #undef OS_ATTR

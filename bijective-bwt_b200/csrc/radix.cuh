@@ -1,11 +1,11 @@
 // radix.cuh -- LSD "onesweep" radix sort of (u64 key, u32 value) pairs, 8-bit digits.
 //
-// One launch per digit.  CTA b owns tile b (tiles are dispatched in index order), ranks its
-// keys with warp-level ballot masks into per-warp digit counters, publishes the tile's
-// 256 digit counts, resolves its global offsets by decoupled look-back over the earlier
-// tiles' status words (single 64-bit words carrying epoch | flag | count, so no reset
-// between passes), stages keys and values through shared memory in tile-sorted order
-// and writes every digit run with consecutive threads on consecutive addresses.
+// One launch per digit.  CTA b owns tile b (tiles are dispatched in index order): the raw tile
+// is bulk-copied into shared memory, the keys are ranked by their digit byte with warp-level
+// ballot masks into per-warp digit counters, the tile's 256 digit counts are published, the
+// global offsets come from a decoupled look-back over the earlier tiles' status words (single
+// 64-bit words carrying epoch | flag | count, so no reset between passes), and every digit run
+// is written with consecutive threads on consecutive addresses.
 //
 // The digit histograms of all passes are taken up front in one sweep (k_radix_hist).
 #pragma once
@@ -15,9 +15,7 @@
 #define RADIX_BINS 256
 #define RADIX_MAX_PASSES 8
 
-#define OS_TILE_MAX 4096          // status array is sized for the smallest tile in use (2048)
-#define OS_TILE_MIN 2048
-#define OS_LOOKBACK 8             // status words fetched per look-back step
+#define OS_TILE_MIN 2048          // the status array is sized for the smallest tile a configuration may use
 
 #define OS_FLAG_AGG 1ull
 #define OS_FLAG_PREFIX 2ull
@@ -78,106 +76,130 @@ __global__ void __launch_bounds__(256) k_radix_hist_scan(u32 *__restrict__ ghist
 
 // ---- one onesweep pass -----------------------------------------------------------------
 // vin == nullptr means "values are the element indices" (first pass of the initial sort).
-// NT threads x IPT keys per thread = one tile; MINB = CTAs per SM the register budget allows;
-// LB = status words fetched per look-back step.
+// K = key type: u64 for the sorts of the doubling, u32 for the binning passes of the rank
+// scatter and of the large-output emit.  NT threads x IPT keys per thread = one tile; MINB = CTAs
+// per SM; LB = status words fetched per look-back step.
 //
-// Shape of the kernel, and what the per-phase cycle counters (OS_PROFILE_PHASES,
-// tests/bench_onesweep.cu) said about the first version (512 x 8, MATCH.ANY ranking, atomic
-// ticket, 29 k cycles per 4096-key tile on uniform digits):
-//   * ranking took 7.3 k cycles: MATCH.ANY occupies its unit for ~100 cycles per warp
-//     instruction when the 32 digits differ.  Peers are now the AND over the 8 digit bits of
-//     (ballot of the bit, complemented where my bit is 0): fixed cost, 4.1 k cycles.
-//   * the ticket (an exposed L2 atomic round trip, 1.6 k cycles) is gone: tile = blockIdx.x.
-//     CTAs are dispatched in index order -- the assumption cub::DeviceScan's look-back makes
-//     as well -- so every tile a look-back waits for is resident or finished.
-//   * the look-back (5.5 k cycles) is mostly a wait for the slowest of the ~85 predecessor
-//     tiles that have no prefix yet, not for status loads: windows of 16 or 32 words, a
-//     cooperative two-group window and a flag-word + 16-bit-aggregate-row protocol all
-//     measured slower or equal.  It runs after keys and values have left
-//     the registers for shared memory -- that staging needs only tile-local offsets.
-//   * three CTAs of 384 threads per SM (56 registers) overlap the phases better than two of 512.
-static __device__ __forceinline__ u64 ldg_stream_key(const u64 *p) { return ldg_stream_u64(p); }
-static __device__ __forceinline__ u32 ldg_stream_key(const u32 *p) { return ldg_stream_u32(p); }
-
-// K = key type: u64 for the sorts of the doubling, u32 for the binning pass of the rank scatter
+// Shape of the kernel (per-phase cycle counters: -DOS_PROFILE_PHASES, tests/bench_onesweep.cu;
+// the history of the numbers is in DESIGN.md sections 4.4 / 4.5):
+//   * the raw tile lands in shared memory through two bulk copies (cp.async.bulk = the TMA unit,
+//     completion counted on an mbarrier) issued by one thread.  Keys and values never occupy
+//     registers: the first version held 8 of each per thread from the load to the staging
+//     (56 registers, 3 CTAs of 3072 keys per SM, 44 % of the HBM peak); this one runs 3 CTAs of
+//     4608 keys at the same register count and 54-56 %.
+//   * ranking reads only the digit byte of each key.  Peers of a key = AND over the 8 digit bits
+//     of (ballot of the bit, complemented where my bit is 0): MATCH.ANY held its unit ~100 cycles
+//     per warp instruction when the 32 digits differ (7.3 k of 29 k cycles per tile).
+//   * tile = blockIdx.x.  CTAs are dispatched in index order -- the assumption cub::DeviceScan's
+//     look-back makes as well -- so every tile a look-back waits for is resident or finished;
+//     an atomic ticket was an exposed L2 round trip per tile.
+//   * the tile-sorted order is a 16-bit permutation (sorted slot -> raw position); the write
+//     phase gathers keys and values through it, consecutive threads on consecutive addresses
+//     of every digit run.
+//   * decoupled look-back with single 64-bit status words (epoch | flag | count, no reset between
+//     passes).  Bigger tiles mean fewer tiles in flight and a shorter walk; windows of 4 words beat
+//     8 and 16 (a wider window mostly fetches words behind the tile that ends the walk).
 template <typename K, int NT, int IPT>
 struct OsSmem {
     static constexpr int TILE = NT * IPT, NW = NT / 32;
-    static constexpr size_t keys = 0;                                   // K[TILE]
-    static constexpr size_t vals = keys + sizeof(K) * TILE;             // u32[TILE]
-    static constexpr size_t wcnt = vals + sizeof(u32) * TILE;           // u16[NW][256]
-    static constexpr size_t dstart = wcnt + sizeof(u16) * NW * RADIX_BINS;  // u32[256]
-    static constexpr size_t adj = dstart + sizeof(u32) * RADIX_BINS;    // u32[256]
-    static constexpr size_t wsum = adj + sizeof(u32) * RADIX_BINS;      // u32[8]
-    static constexpr size_t bytes = wsum + sizeof(u32) * 8;
+    static constexpr size_t keys = 0;                                    // K[TILE], raw order
+    static constexpr size_t vals = keys + sizeof(K) * TILE;              // u32[TILE], raw order
+    static constexpr size_t inv = vals + sizeof(u32) * TILE;             // u16[TILE]: sorted slot -> raw position
+    static constexpr size_t wcnt = inv + sizeof(u16) * TILE;             // u16[NW][256]
+    static constexpr size_t dstart = wcnt + sizeof(u16) * NW * RADIX_BINS;   // u32[256]
+    static constexpr size_t adj = dstart + sizeof(u32) * RADIX_BINS;     // u32[256]
+    static constexpr size_t wsum = adj + sizeof(u32) * RADIX_BINS;       // u32[8]
+    static constexpr size_t mbar = wsum + sizeof(u32) * 8;               // u64
+    static constexpr size_t bytes = mbar + 16;
 };
+
+static __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
 template <typename K, int NT, int IPT, int MINB, int LB>
 __global__ void __launch_bounds__(NT, MINB)
 k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__restrict__ kout,
-                u32 *__restrict__ vout, u32 m, u32 shift, const u32 *__restrict__ binbase,
-                u64 *__restrict__ status, u32 epoch)
+                  u32 *__restrict__ vout, u32 m, u32 shift, const u32 *__restrict__ binbase,
+                  u64 *__restrict__ status, u32 epoch)
 {
     using L = OsSmem<K, NT, IPT>;
     constexpr int TILE = L::TILE, NW = L::NW;
-    static_assert(NT >= RADIX_BINS && TILE <= 65536, "one thread per digit; 16-bit tile positions");
-    extern __shared__ __align__(16) u8 smem[];
+    static_assert(NT >= RADIX_BINS && TILE <= 65536 && IPT % 4 == 0, "one thread per digit; 16-bit tile positions");
+    extern __shared__ __align__(128) u8 smem[];
     K *s_keys = (K *)(smem + L::keys);
     u32 *s_vals = (u32 *)(smem + L::vals);
+    u16 *s_inv = (u16 *)(smem + L::inv);
     u16(*s_wcnt)[RADIX_BINS] = (u16(*)[RADIX_BINS])(smem + L::wcnt);
     u32 *s_dstart = (u32 *)(smem + L::dstart);
     u32 *s_adj = (u32 *)(smem + L::adj);
     u32 *s_wsum = (u32 *)(smem + L::wsum);
+    const u32 mbar = smem_addr(smem + L::mbar);
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     OS_PHASE_INIT();
-    for (u32 i = tid; i < NW * RADIX_BINS / 2; i += NT) ((u32 *)s_wcnt)[i] = 0;
-    __syncthreads();
-    OS_PHASE(0);
     const u32 tile = blockIdx.x;
     const u32 base = tile * TILE;
     const u32 cnt = min((u32)TILE, m - base);
-    const u32 wbase = base + warp * (32 * IPT);
+    const bool bulk = cnt == (u32)TILE;
 
-    // warp-striped loads: slot j of lane l is tile position warp*32*IPT + j*32 + l
-    K key[IPT];
-    u32 val[IPT];
-#pragma unroll
-    for (int j = 0; j < IPT; j++) {
-        const u32 g = wbase + j * 32 + lane;
-        key[j] = (g < m) ? ldg_stream_key(kin + g) : (K)~(K)0;  // pads: digit 255, last in tile order
+    if (tid == 0 && bulk) {
+        const u32 kbytes = (u32)(sizeof(K) * TILE), vbytes = vin ? (u32)(sizeof(u32) * TILE) : 0u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(kbytes + vbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(s_keys)), "l"(kin + base), "r"(kbytes), "r"(mbar) : "memory");
+        if (vin)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr(s_vals)), "l"(vin + base), "r"(vbytes), "r"(mbar) : "memory");
     }
-#pragma unroll
-    for (int j = 0; j < IPT; j++) {
-        const u32 g = wbase + j * 32 + lane;
-        val[j] = (g < m) ? (vin ? ldg_stream_u32(vin + g) : g) : 0u;
+    for (u32 i = tid; i < NW * RADIX_BINS / 2; i += NT) ((u32 *)s_wcnt)[i] = 0;
+    if (!bulk) {  // last tile: plain loads, pads = all ones (digit 255, last in tile order)
+        for (u32 p = tid; p < (u32)TILE; p += NT) {
+            s_keys[p] = (p < cnt) ? kin[base + p] : (K)~(K)0;
+            if (vin) s_vals[p] = (p < cnt) ? vin[base + p] : 0u;
+        }
     }
-#ifdef BWTS_PROFILE_PHASES
-    if (key[IPT - 1] == (K)0x123456789abcdefull && val[IPT - 1] == 0x1234567u) g_phase[15] = 1;  // wait for the loads
-#endif
+    __syncthreads();  // counters zeroed, barrier initialised (or the plain loads done)
+    OS_PHASE(0);
+    if (bulk) {
+        u32 done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar) : "memory");
+    }
     OS_PHASE(1);
 
-    // rank inside the warp, in slot order (stable)
+    // rank inside the warp, in slot order (stable): only the digit byte of each key is read
     u16 *wc = s_wcnt[warp];
     const u32 lt = lanemask_lt();
+    const u32 wpos = warp * (32 * IPT) + lane;  // raw position of my slot 0; slot j is 32 further each
+    const u8 *dbytes = (const u8 *)s_keys + (shift >> 3);
+    const bool bytewise = (shift & 7u) == 0;
+    u32 dpk[IPT / 4];  // my digits, 4 per word
     u16 rnk[IPT];
     {
-        u32 peers[IPT];  // lanes whose digit equals mine
+        u32 peers[IPT];
 #pragma unroll
         for (int j = 0; j < IPT; j++) {
-            const u32 dj = (u32)(key[j] >> shift) & (RADIX_BINS - 1);
+            // byte-aligned digits (all LSD passes) cost one byte load; the binning passes use an
+            // arbitrary shift and read the whole key
+            const u32 dj = bytewise ? (u32)dbytes[(size_t)(wpos + j * 32) * sizeof(K)]
+                                    : ((u32)(s_keys[wpos + j * 32] >> shift) & (RADIX_BINS - 1));
+            if ((j & 3) == 0) dpk[j >> 2] = 0;
+            dpk[j >> 2] |= dj << (8 * (j & 3));
             u32 p = FULL_MASK;
 #pragma unroll
             for (int b = 0; b < RADIX_BITS; b++) {
                 const u32 bit = (dj >> b) & 1u;
                 const u32 bal = __ballot_sync(FULL_MASK, bit);
-                p &= bal ^ (bit - 1u);  // lanes whose bit b equals mine
+                p &= bal ^ (bit - 1u);
             }
             peers[j] = p;
         }
 #pragma unroll
         for (int j = 0; j < IPT; j++) {
-            const u32 dj = (u32)(key[j] >> shift) & (RADIX_BINS - 1);
+            const u32 dj = (dpk[j >> 2] >> (8 * (j & 3))) & 255u;
             const int leader = __ffs(peers[j]) - 1;
             u32 before = 0;
             if ((int)lane == leader) {
@@ -193,7 +215,6 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
     __syncthreads();
     OS_PHASE(3);
 
-    // one thread per digit: exclusive offsets of the warps, tile count, publish the aggregate
     u32 blockcnt = 0, dsum = 0;
     const u32 d = tid;
     u64 *my = status + (u64)tile * RADIX_BINS + d;
@@ -207,29 +228,26 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
         st_relaxed_u64(my, os_pack(epoch, tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG, blockcnt));
         const u32 incl = warp_incl_sum(blockcnt);
         if (lane == 31) s_wsum[warp] = incl;
-        dsum = incl - blockcnt;  // exclusive sum inside my warp of digits
+        dsum = incl - blockcnt;
     }
     __syncthreads();
     if (tid < RADIX_BINS) {
 #pragma unroll
         for (int w = 0; w < RADIX_BINS / 32; w++)
             if (w < (int)warp) dsum += s_wsum[w];
-        s_dstart[d] = dsum;  // where the digit's run starts inside the sorted tile
+        s_dstart[d] = dsum;
     }
     __syncthreads();
     OS_PHASE(4);
 
-    // keys and values -> shared memory in tile-sorted order (frees their registers)
+    // the tile-sorted order as a permutation: sorted slot -> raw position
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
-        const u32 dj = (u32)(key[j] >> shift) & (RADIX_BINS - 1);
-        const u32 pos = s_dstart[dj] + wc[dj] + rnk[j];
-        s_keys[pos] = key[j];
-        s_vals[pos] = val[j];
+        const u32 dj = (dpk[j >> 2] >> (8 * (j & 3))) & 255u;
+        s_inv[s_dstart[dj] + wc[dj] + rnk[j]] = (u16)(wpos + j * 32);
     }
     OS_PHASE(5);
 
-    // decoupled look-back over the earlier tiles, LB status words per step
     if (tid < RADIX_BINS) {
         u32 excl = 0;
         if (tile != 0) {
@@ -246,8 +264,8 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
                 int used = 0;
 #pragma unroll
                 for (int q = 0; q < LB; q++) {
-                    if (found || used != q) continue;          // stopped earlier in this window
-                    if ((u32)(v[q] >> 34) != epoch) continue;  // not published yet: re-read from here
+                    if (found || used != q) continue;
+                    if ((u32)(v[q] >> 34) != epoch) continue;
                     excl += (u32)v[q];
                     used = q + 1;
                     if (((v[q] >> 32) & 3ull) == OS_FLAG_PREFIX) found = true;
@@ -262,17 +280,16 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
     __syncthreads();
     OS_PHASE(7);
 
-    // every digit run goes out with consecutive threads on consecutive addresses
 #pragma unroll
     for (int q = 0; q < IPT; q++) {
         const u32 s = q * NT + tid;
         if (s < cnt) {
-            const K k = s_keys[s];
+            const u32 p = s_inv[s];
+            const K k = s_keys[p];
             const u32 dst = s + s_adj[(u32)(k >> shift) & (RADIX_BINS - 1)];
             kout[dst] = k;
-            vout[dst] = s_vals[s];
+            vout[dst] = vin ? s_vals[p] : base + p;
         }
     }
     OS_PHASE(8);
 }
-

@@ -183,8 +183,14 @@ int main(int argc, char **argv)
         k_gen<<<(m + 255) / 256, 256>>>(b.orig, m, dist, 42);
         CHECK(cudaDeviceSynchronize());
 #define RUN(NT, IPT, MINB, LB) run_config<NT, IPT, MINB, LB>(#NT "x" #IPT " minb" #MINB " lb" #LB, b, m, reps, dist)
-        RUN(384, 8, 3, 8);
-        RUN(512, 8, 2, 8);
+        RUN(384, 12, 3, 4);
+        RUN(384, 12, 3, 2);
+        RUN(384, 12, 3, 3);
+        RUN(384, 12, 3, 6);
+        RUN(384, 12, 3, 8);
+        RUN(512, 8, 3, 4);
+        RUN(256, 16, 3, 4);
+        RUN(352, 12, 3, 4);
 #undef RUN
     }
     return 0;
