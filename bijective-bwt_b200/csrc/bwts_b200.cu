@@ -227,7 +227,8 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
         case 1: OS_LAUNCH(512, 8, 3, 8); break;
         case 2: OS_LAUNCH(256, 16, 3, 8); break;
         case 3: OS_LAUNCH(384, 12, 3, 8); break;
-        default: OS_LAUNCH(384, 12, 3, 4); break;
+        case 4: OS_LAUNCH(384, 12, 3, 4); break;
+        default: OS_LAUNCH(384, 12, 3, 2); break;
         }
 #undef OS_LAUNCH
         sb.cur = b;
@@ -714,6 +715,7 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     cudaFuncSetAttribute(k_onesweep_pass<K_, NT_, IPT_, MINB_, LB_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
     OS_ATTR(u64, 384, 12, 3, 4);
     OS_ATTR(u64, 384, 12, 3, 8);
+    OS_ATTR(u64, 384, 12, 3, 2);
     OS_ATTR(u64, 512, 8, 3, 8);
     OS_ATTR(u64, 256, 16, 3, 8);
     OS_ATTR(u32, 384, 12, 3, 4);
@@ -1188,7 +1190,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 1) { if (value != 0 && (value < 20 || value > 31)) return BWTS_B200_EINVAL; g_tune_spl_shift = value; return 0; }
     if (key == 3) { g_tune_local = value; return 0; }
     if (key == 4) { g_tune_lyndon = value; return 0; }
-    if (key == 2) { if (value < 0 || value > 3) return BWTS_B200_EINVAL; g_tune_onesweep = value; return 0; }
+    if (key == 2) { if (value < 0 || value > 4) return BWTS_B200_EINVAL; g_tune_onesweep = value; return 0; }
     if (key == 5) { g_tune_pipeline = value; return 0; }
     if (key == 6) { g_tune_keybits = value; return 0; }
     if (key == 7) { g_tune_scatterbin = value; return 0; }

@@ -97,8 +97,10 @@ __global__ void __launch_bounds__(256) k_radix_hist_scan(u32 *__restrict__ ghist
 //     phase gathers keys and values through it, consecutive threads on consecutive addresses
 //     of every digit run.
 //   * decoupled look-back with single 64-bit status words (epoch | flag | count, no reset between
-//     passes).  Bigger tiles mean fewer tiles in flight and a shorter walk; windows of 4 words beat
-//     8 and 16 (a wider window mostly fetches words behind the tile that ends the walk).
+//     passes).  Bigger tiles mean fewer tiles in flight and a shorter walk; windows of 2-4 words beat
+//     8 and 16 (a wider window mostly fetches words behind the tile that ends the walk).  With every
+//     tile's prefix handed to it (ORACLE, timing only) the pass runs 10 % faster: that is all the
+//     look-back still costs.
 template <typename K, int NT, int IPT>
 struct OsSmem {
     static constexpr int TILE = NT * IPT, NW = NT / 32;
@@ -115,7 +117,7 @@ struct OsSmem {
 
 static __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
-template <typename K, int NT, int IPT, int MINB, int LB>
+template <typename K, int NT, int IPT, int MINB, int LB, bool ORACLE = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__restrict__ kout,
                   u32 *__restrict__ vout, u32 m, u32 shift, const u32 *__restrict__ binbase,
@@ -225,7 +227,7 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
             s_wcnt[w][d] = (u16)blockcnt;
             blockcnt += c;
         }
-        st_relaxed_u64(my, os_pack(epoch, tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG, blockcnt));
+        if (!ORACLE) st_relaxed_u64(my, os_pack(epoch, tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG, blockcnt));
         const u32 incl = warp_incl_sum(blockcnt);
         if (lane == 31) s_wsum[warp] = incl;
         dsum = incl - blockcnt;
@@ -250,7 +252,11 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
 
     if (tid < RADIX_BINS) {
         u32 excl = 0;
-        if (tile != 0) {
+        if (ORACLE) {
+            // timing experiment (tests/bench_onesweep.cu): the prefix this tile published in an identical
+            // earlier launch is still in its status word -- the kernel without any look-back
+            excl = (u32)ld_relaxed_u64(my) - blockcnt;
+        } else if (tile != 0) {
             int t = (int)tile - 1;
             bool found = false;
             while (!found) {

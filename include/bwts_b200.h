@@ -126,7 +126,7 @@ const char *bwts_b200_version(void);
 
 /* Test hooks: override tuning constants so that small inputs exercise the multi-tile /
  * multi-chunk paths.  key: 0 = Lyndon chunk bytes (>= 1), 1 = inverse splitter shift
- * (density 2^-(32-shift), 20..31), 2 = onesweep tile shape (0..3), 3 = disable the
+ * (density 2^-(32-shift), 20..31), 2 = onesweep tile shape (0..4), 3 = disable the
  * warp-local sort path (1), 4 = force the suffix-sort fallback for the Lyndon boundaries (1),
  * 5 = no copy/compute overlap between the blocks of one device (1), 6 = cap on the bits of
  * the initial packed key (8..64), 7 = binned rank scatter of the first re-rank (1 = never,
