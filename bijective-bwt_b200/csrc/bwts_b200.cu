@@ -71,7 +71,15 @@ struct bwts_b200_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_io0 = nullptr, ev_io1 = nullptr;
     bwts_b200_stats stats;
     u32 epoch = 0;
+    // block pipeline state, created on first use and kept: cudaMalloc / cudaFree of the GiB-sized
+    // I/O slots cost 100-700 ms per call when something polls the driver (nvidia-smi -lms)
+    u8 *pipe_io = nullptr;
+    size_t pipe_io_bytes = 0;
+    cudaStream_t pipe_s_in = nullptr, pipe_s_out = nullptr;
+    cudaEvent_t pipe_ev_loaded[2] = {nullptr, nullptr};
+    struct PinnedRing *pipe_ring_in = nullptr, *pipe_ring_out = nullptr;
 };
+static void pipe_state_destroy(bwts_b200_ctx *ctx);
 
 #define CK(call)                                                                  \
     do {                                                                          \
@@ -746,6 +754,7 @@ extern "C" void bwts_b200_destroy(bwts_b200_ctx *ctx)
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->ev_io0) cudaEventDestroy(ctx->ev_io0);
     if (ctx->ev_io1) cudaEventDestroy(ctx->ev_io1);
+    pipe_state_destroy(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     delete ctx;
@@ -911,6 +920,17 @@ struct PinnedRing {
     }
 };
 
+static void pipe_state_destroy(bwts_b200_ctx *ctx)
+{
+    if (ctx->pipe_ring_in) { ctx->pipe_ring_in->destroy(); delete ctx->pipe_ring_in; ctx->pipe_ring_in = nullptr; }
+    if (ctx->pipe_ring_out) { ctx->pipe_ring_out->destroy(); delete ctx->pipe_ring_out; ctx->pipe_ring_out = nullptr; }
+    for (int i = 0; i < 2; i++)
+        if (ctx->pipe_ev_loaded[i]) { cudaEventDestroy(ctx->pipe_ev_loaded[i]); ctx->pipe_ev_loaded[i] = nullptr; }
+    if (ctx->pipe_s_in) { cudaStreamDestroy(ctx->pipe_s_in); ctx->pipe_s_in = nullptr; }
+    if (ctx->pipe_s_out) { cudaStreamDestroy(ctx->pipe_s_out); ctx->pipe_s_out = nullptr; }
+    if (ctx->pipe_io) { cudaFree(ctx->pipe_io); ctx->pipe_io = nullptr; ctx->pipe_io_bytes = 0; }
+}
+
 // host -> device, through the ring when the source is pageable; returns after the copies are ISSUED
 static int pipe_h2d(PinnedRing &ring, bool pinned, u8 *d_dst, const u8 *src, size_t len, cudaStream_t st, size_t &seq)
 {
@@ -985,22 +1005,36 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     const bool in_pinned = host_ptr_is_pinned(in), out_pinned = host_ptr_is_pinned(out);
     const size_t slot_bytes = ((size_t)block_len + 255) & ~(size_t)255;
-    u8 *d_io = nullptr;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_loaded[2] = {nullptr, nullptr};
-    PinnedRing ring_in, ring_out;
     std::atomic<int> status{0};
     auto fail = [&](int rc) { int z = 0; status.compare_exchange_strong(z, rc); };
 
     int rc = arena_reserve(ctx, workspace_bytes((size_t)block_len));
-    if (rc == 0 && cudaMalloc((void **)&d_io, 4 * slot_bytes) != cudaSuccess) { cudaGetLastError(); rc = BWTS_B200_ENOMEM; }
-    if (rc == 0 && (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
-                    cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&ev_loaded[0], cudaEventDisableTiming) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&ev_loaded[1], cudaEventDisableTiming) != cudaSuccess))
+    if (rc == 0 && ctx->pipe_io_bytes < 4 * slot_bytes) {
+        if (ctx->pipe_io) { cudaFree(ctx->pipe_io); ctx->pipe_io = nullptr; ctx->pipe_io_bytes = 0; }
+        if (cudaMalloc((void **)&ctx->pipe_io, 4 * slot_bytes) != cudaSuccess) { cudaGetLastError(); rc = BWTS_B200_ENOMEM; }
+        else ctx->pipe_io_bytes = 4 * slot_bytes;
+    }
+    if (rc == 0 && !ctx->pipe_s_in &&
+        (cudaStreamCreateWithFlags(&ctx->pipe_s_in, cudaStreamNonBlocking) != cudaSuccess ||
+         cudaStreamCreateWithFlags(&ctx->pipe_s_out, cudaStreamNonBlocking) != cudaSuccess ||
+         cudaEventCreateWithFlags(&ctx->pipe_ev_loaded[0], cudaEventDisableTiming) != cudaSuccess ||
+         cudaEventCreateWithFlags(&ctx->pipe_ev_loaded[1], cudaEventDisableTiming) != cudaSuccess))
         rc = BWTS_B200_ECUDA;
-    if (rc == 0 && !in_pinned) rc = ring_in.init();
-    if (rc == 0 && !out_pinned) rc = ring_out.init();
+    if (rc == 0 && !in_pinned && !ctx->pipe_ring_in) {
+        ctx->pipe_ring_in = new PinnedRing();
+        rc = ctx->pipe_ring_in->init();
+    }
+    if (rc == 0 && !out_pinned && !ctx->pipe_ring_out) {
+        ctx->pipe_ring_out = new PinnedRing();
+        rc = ctx->pipe_ring_out->init();
+    }
+    u8 *d_io = ctx->pipe_io;
+    cudaStream_t s_in = ctx->pipe_s_in, s_out = ctx->pipe_s_out;
+    cudaEvent_t *ev_loaded = ctx->pipe_ev_loaded;
+    PinnedRing dummy_ring;
+    PinnedRing &ring_in = ctx->pipe_ring_in ? *ctx->pipe_ring_in : dummy_ring;
+    PinnedRing &ring_out = ctx->pipe_ring_out ? *ctx->pipe_ring_out : dummy_ring;
+    for (int c = 0; c < PIPE_NCHUNK; c++) { ring_in.busy[c] = false; }
     if (dbg) fprintf(stderr, "[pipe dev %d] setup %.2f ms (pinned in/out %d/%d, %zu blocks)\n", dev, since(), (int)in_pinned, (int)out_pinned, mine.size());
     if (rc == 0) {
         u8 *d_in[2] = {d_io, d_io + slot_bytes}, *d_out[2] = {d_io + 2 * slot_bytes, d_io + 3 * slot_bytes};
@@ -1055,14 +1089,8 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
         rc = status.load();
     }
     if (dbg) fprintf(stderr, "[pipe dev %d] pipeline done at %.2f ms\n", dev, since());
-    cudaDeviceSynchronize();
-    ring_in.destroy();
-    ring_out.destroy();
-    if (ev_loaded[0]) cudaEventDestroy(ev_loaded[0]);
-    if (ev_loaded[1]) cudaEventDestroy(ev_loaded[1]);
-    if (s_in) cudaStreamDestroy(s_in);
-    if (s_out) cudaStreamDestroy(s_out);
-    if (d_io) cudaFree(d_io);
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_out);
     if (dbg) fprintf(stderr, "[pipe dev %d] teardown done at %.2f ms\n", dev, since());
     return rc;
 }

@@ -80,8 +80,8 @@ def test_golden_small_with_tiny_chunks(bwts, ctx, gen, chunk, shift):
             assert helpers.sha256(inv) == v["inv_sha256"], v["name"]
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 2047, 2048, 2049, 4095, 4096, 4097, 8191, 8192, 8193,
-                               65535, 65536, 65537])
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 2047, 2048, 2049, 4095, 4096, 4097, 4607, 4608, 4609,
+                               8191, 8192, 8193, 9216, 65535, 65536, 65537, 14 * 4608])  # 4608 = onesweep tile
 def test_families_at_tile_edges(bwts, ctx, oracle, n):
     bwts.tune(0, 512)
     bwts.tune(1, 29)
