@@ -276,3 +276,71 @@ def inverse(Bs, shift=26):
             pos = n - 1 - offs[s] - d
         out[pos] = B[i]
     return out.tobytes()
+
+
+# ---- models of the round-1b kernels --------------------------------------------------------------
+
+def owned_ranges(gst, T):
+    """Ownership rule of k_local_sort_warp (T = 32) and k_local_sort_cta (T = 4096): worker c owns
+    the whole groups between the group holding live slot c*T and the group holding slot (c+1)*T.
+    gst[j] = live-array offset at which the group of slot j starts.  Returns [(lo, hi)]."""
+    m = len(gst)
+    out = []
+    for c in range((m + T - 1) // T):
+        lo = int(gst[c * T])
+        hi = int(gst[(c + 1) * T]) if (c + 1) * T < m else m
+        out.append((lo, hi))
+    return out
+
+
+def cta_sort_key(g_local, r, slot):
+    """64-bit word ordered by the bitonic network of k_local_sort_cta: local group start (13 bits) |
+    key2 (31 bits) | slot (13 bits)."""
+    return (int(g_local) << 44) | (int(r) << 13) | int(slot)
+
+
+def bitonic_sort(a):
+    """the compare-exchange schedule of k_local_sort_cta (strides >= 8 in shared memory, smaller ones
+    in registers -- the order of the exchanges is the same) on a power-of-two list"""
+    a = list(a)
+    P = len(a)
+    k2 = 2
+    while k2 <= P:
+        j = k2 >> 1
+        while j > 0:
+            for t in range(P // 2):
+                i = ((t & ~(j - 1)) << 1) | (t & (j - 1))
+                l = i + j
+                up = (i & k2) == 0
+                if (a[i] > a[l]) == up:
+                    a[i], a[l] = a[l], a[i]
+            j >>= 1
+        k2 <<= 1
+    return a
+
+
+def binned_scatter(pos, val, n, kb):
+    """first re-rank / large emit: pairs binned (stably) by the top 8 bits of the target position,
+    then scattered bin by bin; must equal the direct scatter"""
+    shift = kb - 8
+    order = np.argsort(pos >> shift, kind="stable")
+    out = np.zeros(n, dtype=val.dtype)
+    out[pos[order]] = val[order]
+    return out
+
+
+def onesweep_tile_permutation(digits):
+    """k_onesweep_pass: sorted slot -> raw position of one tile (stable by digit), built the way the
+    kernel does: per-warp ranks in slot order, exclusive warp offsets per digit, digit starts"""
+    TILE = len(digits)
+    inv = np.full(TILE, -1, dtype=np.int64)
+    counts = np.bincount(digits, minlength=256)
+    dstart = np.concatenate(([0], np.cumsum(counts)[:-1]))
+    seen = np.zeros(256, dtype=np.int64)
+    # warp-striped slots visit raw positions in increasing order per warp and the warps' counters are
+    # offset by the earlier warps' totals, so the net effect is "stable by digit in raw order"
+    for p in range(TILE):
+        d = digits[p]
+        inv[dstart[d] + seen[d]] = p
+        seen[d] += 1
+    return inv

@@ -35,3 +35,67 @@ def test_splitter_inverse(oracle):
     for name, x in _cases():
         for shift in (26, 30, 31):
             assert model.inverse(x, shift=shift) == oracle.inverse(x), (name, shift)
+
+
+def test_ownership_rule_partitions_groups():
+    """every group is owned by exactly one worker, and a worker's share is < 2T slots when no
+    group has more than T members (k_local_sort_warp: T = 32, k_local_sort_cta: T = 4096)"""
+    rng = np.random.default_rng(7)
+    for T in (4, 32, 100):
+        for _ in range(50):
+            sizes = rng.integers(1, T + 1, size=int(rng.integers(1, 60)))
+            starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+            gst = np.repeat(starts, sizes)
+            ranges = model.owned_ranges(gst, T)
+            covered = np.zeros(len(gst), dtype=np.int64)
+            for lo, hi in ranges:
+                assert hi - lo < 2 * T
+                assert lo == len(gst) or gst[lo] == lo          # starts at a group head
+                assert hi == len(gst) or gst[hi] == hi          # ends at a group head
+                covered[lo:hi] += 1
+            assert (covered == 1).all()
+    # an oversize group shows up as a share > 2T - 1 somewhere (what k_ls_probe looks for)
+    gst = np.zeros(1000, dtype=np.int64)
+    assert max(hi - lo for lo, hi in model.owned_ranges(gst, 32)) >= 64
+
+
+def test_cta_sort_word_orders_by_group_key_slot():
+    rng = np.random.default_rng(8)
+    for _ in range(20):
+        cnt = int(rng.integers(2, 200))
+        sizes = []
+        while sum(sizes) < cnt:
+            sizes.append(int(rng.integers(1, 40)))
+        sizes[-1] -= sum(sizes) - cnt
+        starts = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int64)
+        g = np.repeat(starts, sizes)
+        r = rng.integers(0, 1 << 31, size=cnt)
+        r[rng.integers(0, cnt, size=cnt // 3)] = r[0]  # ties
+        words = [model.cta_sort_key(g[s], r[s], s) for s in range(cnt)]
+        P = 1
+        while P < cnt:
+            P <<= 1
+        got = model.bitonic_sort(words + [(1 << 64) - 1] * (P - cnt))[:cnt]
+        want = sorted(range(cnt), key=lambda s: (g[s], r[s], s))
+        assert [w & 8191 for w in got] == want
+        # groups stay where they were: slot s of the output belongs to the group that owned slot s
+        assert [(w >> 44) for w in got] == g.tolist()
+
+
+def test_binned_scatter_equals_direct_scatter():
+    rng = np.random.default_rng(9)
+    for n in (256, 1000, 70_001):
+        kb = max(8, int(n - 1).bit_length())
+        pos = rng.permutation(n).astype(np.int64)
+        val = rng.integers(0, 1 << 30, size=n)
+        direct = np.zeros(n, dtype=val.dtype)
+        direct[pos] = val
+        assert np.array_equal(model.binned_scatter(pos, val, n, kb), direct)
+
+
+def test_onesweep_tile_permutation_is_the_stable_partition():
+    rng = np.random.default_rng(10)
+    for tile in (384 * 12, 100):
+        digits = rng.integers(0, 256, size=tile)
+        inv = model.onesweep_tile_permutation(digits)
+        assert np.array_equal(inv, np.argsort(digits, kind="stable"))
