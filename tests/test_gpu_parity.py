@@ -170,6 +170,22 @@ def test_blocks_equal_concatenated_single_blocks(bwts, oracle, gen):
     assert bwts.forward_blocks(x, 0) == oracle.forward(x)
 
 
+def test_onesweep_tile_shapes(bwts, ctx, oracle, gen):
+    """every compiled shape of the onesweep kernel (tune 2: 0 = 384x12 with a 2-word look-back
+    window, 1 = 512x8, 2 = 256x16, 3 / 4 = 384x12 with 8 / 4 words) sorts identically"""
+    cases = [gen.make("text", 95, 1_300_000), gen.make("random", 96, 300_000), helpers.families(70_001)["ww"],
+             helpers.families(4608 * 3)["random4"]]
+    try:
+        for shape in (1, 2, 3, 4, 0):
+            bwts.tune(2, shape)
+            bwts.tune(8, 1)   # keep the large-group set on the radix path so that every round sorts
+            for x in cases:
+                assert ctx.forward_host(x) == oracle.forward(x), (shape, len(x))
+    finally:
+        bwts.tune(2, 0)
+        bwts.tune(8, 0)
+
+
 def test_binned_rank_scatter_forced_on_small_inputs(bwts, ctx, oracle, gen):
     """first re-rank: ranks binned by text region with one u32 onesweep pass, then scattered
     (default for >= 4 Mi bytes); forced here so that few-byte inputs cross the bin edges"""
