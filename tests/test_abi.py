@@ -103,3 +103,17 @@ def test_cli_error_behaviour_equals_reference_binaries(tool, ref, tmp_path):
         a = subprocess.run([str(BIN / tool)] + args, capture_output=True)
         b = subprocess.run([str(helpers.REF_DIR / ref)] + args, capture_output=True)
         assert (a.returncode, a.stdout, a.stderr) == (b.returncode, b.stdout, b.stderr), args
+
+
+def test_stats_struct_layout_matches_the_header(tmp_path):
+    """the ctypes mirror of bwts_b200_stats has the size the C compiler gives the header's struct"""
+    import ctypes
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "bwts_b200.h"\n'
+                   'int main(void){printf("%zu\\n", sizeof(bwts_b200_stats));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-I", str(helpers.REPO / "include"), "-o", str(exe), str(src)])
+    csize = int(subprocess.check_output([str(exe)]).decode())
+    bwts = helpers.load_product()
+    assert csize == ctypes.sizeof(bwts.Stats)
