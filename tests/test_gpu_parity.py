@@ -15,6 +15,8 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "vectors.json").read_text())
+# SHA-256 of the unmodified reference's forward output at the full BASELINE sizes (make_fullsize_golden.py)
+FULLSIZE = json.loads((Path(__file__).parent / "golden" / "fullsize.json").read_text())
 
 
 def golden_input(v, gen):
@@ -126,7 +128,9 @@ def test_full_size_properties_64mib(ctx, gen):
     at this size lives in bench.py's cpu_baseline sample)"""
     n = 64 << 20
     x = gen.make("text", 2, n)
+    assert helpers.sha256(x) == FULLSIZE["C2"]["input_sha256"]
     y = ctx.forward_host(x)
+    assert helpers.sha256(y) == FULLSIZE["C2"]["fwd_sha256"], "differs from the reference's mk_bwts output"
     assert len(y) == n and y[0] == x[-1]
     assert np.array_equal(np.bincount(np.frombuffer(x, np.uint8), minlength=256),
                           np.bincount(np.frombuffer(y, np.uint8), minlength=256))
@@ -137,13 +141,17 @@ def test_full_size_properties_64mib(ctx, gen):
 
 @pytest.mark.parametrize("kind,seed,n", [("tiled", 3, 256 << 20), ("dna", 4, 1 << 30)])
 def test_full_size_properties_c3_c4(bwts, gen, kind, seed, n):
-    """BASELINE configs[2] and configs[3] at full size (256 MiB tiled text, 1 GiB DNA):
-    round trip, out[0] == x[-1], byte histogram; 1 GiB also runs the binned emit"""
+    """BASELINE configs[2] and configs[3] at full size (256 MiB tiled text, 1 GiB DNA): SHA-256 of the
+    forward output equals the unmodified reference's (tests/golden/fullsize.json), round trip,
+    out[0] == x[-1], byte histogram; 1 GiB also runs the binned emit"""
     x = gen.make(kind, seed, n)
+    gold = FULLSIZE["C3" if kind == "tiled" else "C4"]
+    assert gold["n"] == n and helpers.sha256(x) == gold["input_sha256"]
     xa = np.frombuffer(x, np.uint8)
     with bwts.Context(0) as c:
         y = c.forward_host(x)
         st = c.stats()
+        assert helpers.sha256(y) == gold["fwd_sha256"], "differs from the reference's mk_bwts output"
         assert len(y) == n and y[0] == x[-1]
         ya = np.frombuffer(y, np.uint8)
         assert np.array_equal(np.bincount(xa, minlength=256), np.bincount(ya, minlength=256))
