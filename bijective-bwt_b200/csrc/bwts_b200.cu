@@ -45,6 +45,14 @@ static long g_tune_keybits = 0;    // cap on the bits of the initial packed key 
 static long g_tune_emit = 0;       // emit: 0 = binned from 512 Mi bytes, 1 = always rank windows, 2 = always binned
 static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L set
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
+static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
+static long g_tune_nomark = 0;     // TIMING EXPERIMENT ONLY: inverse first walk without visited marks (wrong output when a cycle has no splitter)
+
+static void apply_device_limits()
+{
+    if (g_tune_l2gran == 32 || g_tune_l2gran == 64 || g_tune_l2gran == 128)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g_tune_l2gran);
+}
 
 static bool use_binned_scatter(unsigned n, unsigned kb)
 {
@@ -52,7 +60,7 @@ static bool use_binned_scatter(unsigned n, unsigned kb)
     return g_tune_scatterbin == 2 || n >= (1u << 22);
 }
 
-struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; };
+struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; const char *name = ""; };
 
 struct bwts_b200_ctx {
     int device = 0;
@@ -104,7 +112,7 @@ static cudaEvent_t ctx_event(bwts_b200_ctx *ctx)
 #define LAUNCH(KCLS_, NBYTES_, kern, grid, block, ...)                               \
     do {                                                                             \
         LaunchRec r__;                                                               \
-        r__.cls = (KCLS_); r__.bytes = (double)(NBYTES_); r__.e0 = r__.e1 = nullptr; \
+        r__.cls = (KCLS_); r__.bytes = (double)(NBYTES_); r__.e0 = r__.e1 = nullptr; r__.name = #kern; \
         if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); } \
         kern<<<(grid), (block), 0, st>>>(__VA_ARGS__);                               \
         if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
@@ -129,13 +137,19 @@ static void stats_end(bwts_b200_ctx *ctx, cudaStream_t st)
     cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
     ctx->stats.total_ms = ms;
     ctx->stats.launches = (long)ctx->recs.size();
+    static const bool trace = getenv("BWTS_B200_TRACE") != nullptr;  // one line per launch to stderr
+    int seq = 0;
     for (const LaunchRec &r : ctx->recs) {
         ctx->stats.class_launches[r.cls]++;
         ctx->stats.class_bytes[r.cls] += r.bytes;
+        float t = 0;
         if (r.e0 && r.e1) {
-            float t = 0;
             if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) ctx->stats.class_ms[r.cls] += t;
         }
+        if (trace)
+            fprintf(stderr, "[trace %s n=%ld] %3d %-14s %-24s %9.4f ms %12.0f B %8.1f GB/s\n", ctx->stats.direction ? "inv" : "fwd",
+                    ctx->stats.len, seq, kclass_names[r.cls], r.name, t, r.bytes, t > 0 ? r.bytes / t * 1e-6 : 0.0);
+        seq++;
     }
 }
 
@@ -222,7 +236,7 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
 #define OS_LAUNCH(NT_, IPT_, MINB_, LB_)                                                                  \
     do {                                                                                                  \
         LaunchRec r__;                                                                                    \
-        r__.cls = KC_ONESWEEP; r__.bytes = bytes; r__.e0 = r__.e1 = nullptr;                              \
+        r__.cls = KC_ONESWEEP; r__.bytes = bytes; r__.e0 = r__.e1 = nullptr; r__.name = "k_onesweep_pass<u64>";  \
         if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }           \
         k_onesweep_pass<u64, NT_, IPT_, MINB_, LB_><<<cdiv(m, (NT_) * (IPT_)), NT_, OsSmem<u64, NT_, IPT_>::bytes, st>>>( \
             sb.k[a], vin, sb.k[b], sb.v[b], m, (u32)(p * RADIX_BITS), sb.hist + p * RADIX_BINS, sb.status,  \
@@ -426,7 +440,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             LAUNCH(KC_RERANK, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
             do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
             LaunchRec r__;
-            r__.cls = KC_RERANK; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr;
+            r__.cls = KC_RERANK; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr; r__.name = "k_onesweep_pass<u32> bin";
             if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
             k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(n, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
                 sb.v[sb.cur], nr_buf, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
@@ -512,7 +526,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                 if (rc) return rc;
                 if (ctx->h_small[0] == 0) {
                     LaunchRec r__;
-                    r__.cls = KC_LOCAL_SORT; r__.bytes = 32.0 * mL; r__.e0 = r__.e1 = nullptr;
+                    r__.cls = KC_LOCAL_SORT; r__.bytes = 32.0 * mL; r__.e0 = r__.e1 = nullptr; r__.name = "k_local_sort_cta";
                     if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
                     if (!linear)
                         k_local_sort_cta<false><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
@@ -564,7 +578,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             LAUNCH(KC_EMIT, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
             do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
             LaunchRec r__;
-            r__.cls = KC_EMIT; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr;
+            r__.cls = KC_EMIT; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr; r__.name = "k_onesweep_pass<u32> bin";
             if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
             k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(n, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
                 rank, val, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
@@ -650,7 +664,7 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     if (!visited) return BWTS_B200_EINTERNAL;
     CK(cudaMemsetAsync(visited, 0, ((size_t)(n >> 5) + 2) * 4, st));
     LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
-           visited, small + 2);
+           g_tune_nomark ? (u32 *)nullptr : visited, small + 2);
 
     // -- reduced list: cycle minimum, then distance to the sublist holding it
     const int R = bit_length((u64)ns - 1) + 1;
@@ -782,6 +796,7 @@ static int run_device(bwts_b200_ctx *ctx, int direction, const void *d_in, long 
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->own_stream;
+    apply_device_limits();
     stats_begin(ctx, len, direction, st);
     rc = direction == 0 ? forward_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, nullptr, FWD_BWTS, st)
                         : inverse_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, st);
@@ -818,6 +833,7 @@ static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, 
     ctx->io_in = nullptr;
     u8 *d_in = ctx->arena, *d_out = ctx->arena + ctx->io_bytes;
     cudaStream_t st = ctx->own_stream;
+    apply_device_limits();
     CK(cudaEventRecord(ctx->ev_io0, st));
     CK(cudaMemcpyAsync(d_in, in, (size_t)len, cudaMemcpyHostToDevice, st));
     ctx->io_in = d_in;  // tells the cores to skip the I/O region of the arena
@@ -1224,5 +1240,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 7) { g_tune_scatterbin = value; return 0; }
     if (key == 8) { g_tune_nocta = value; return 0; }
     if (key == 9) { g_tune_emit = value; return 0; }
+    if (key == 10) { g_tune_l2gran = value; return 0; }
+    if (key == 11) { g_tune_nomark = value; return 0; }
     return BWTS_B200_EINVAL;
 }

@@ -74,6 +74,7 @@ def test_block_plans_cover_every_block_once():
     for world in (1, 2, 4, 8):
         seen = []
         for r in range(world):
-            seen += [s for _, s, _ in bench.plan_blocks("C5", r, world)]
+            seen += [s for _, s, _, _ in bench.plan_blocks("C5", r, world)]
         assert sorted(seen) == list(range(50, 58))
-        assert len({s for r in range(world) for _, s, _ in bench.plan_blocks("C2", r, world)}) == world
+        assert len({s for r in range(world) for _, s, _, _ in bench.plan_blocks("C2", r, world)}) == world
+        assert bench.default_workload(world) == ("C4" if world == 1 else "C5")
