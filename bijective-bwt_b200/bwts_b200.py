@@ -16,6 +16,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libbwts_b200.so"
 
 NCLASS = 16
+NPHASE = 8
 MAX_LEN = 1 << 30
 
 EXPORTS = [
@@ -24,7 +25,7 @@ EXPORTS = [
     "bwts_b200_forward_host", "bwts_b200_inverse_host", "bwts_b200_forward_device",
     "bwts_b200_inverse_device", "bwts_b200_get_stats", "bwts_b200_class_name", "bwts_b200_set_profile",
     "bwts_b200_strerror", "bwts_b200_last_cuda_error", "bwts_b200_version", "bwts_b200_tune",
-    "bwts_b200_divsufsort",
+    "bwts_b200_divsufsort", "bwts_b200_phase_name",
 ]
 
 
@@ -46,6 +47,7 @@ class Stats(ctypes.Structure):
         ("class_launches", ctypes.c_long * NCLASS), ("class_ms", ctypes.c_double * NCLASS),
         ("class_bytes", ctypes.c_double * NCLASS),
         ("h2d_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double), ("lyndon_fallback", ctypes.c_int),
+        ("phase_ms", ctypes.c_double * NPHASE), ("arena_bytes", ctypes.c_long), ("first_live", ctypes.c_long),
     ]
 
 
@@ -78,6 +80,8 @@ def lib():
     L.bwts_b200_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.bwts_b200_class_name.argtypes = [ci]
     L.bwts_b200_class_name.restype = ctypes.c_char_p
+    L.bwts_b200_phase_name.argtypes = [ci, ci]
+    L.bwts_b200_phase_name.restype = ctypes.c_char_p
     L.bwts_b200_set_profile.argtypes = [vp, ci]
     L.bwts_b200_strerror.argtypes = [ci]
     L.bwts_b200_strerror.restype = ctypes.c_char_p
@@ -224,7 +228,14 @@ class Context:
     def stats(self):
         s = Stats()
         _check(lib().bwts_b200_get_stats(self._h, ctypes.byref(s)), "bwts_b200_get_stats")
-        out = {f: getattr(s, f) for f, _ in Stats._fields_ if not f.startswith("class_")}
+        out = {f: getattr(s, f) for f, _ in Stats._fields_ if not f.startswith("class_") and f != "phase_ms"}
+        out["arena_bytes_per_byte"] = s.arena_bytes / s.len if s.len else None
+        phases = {}
+        for ph in range(NPHASE):
+            name = lib().bwts_b200_phase_name(s.direction, ph)
+            if name:
+                phases[name.decode()] = s.phase_ms[ph]
+        out["phases"] = phases
         classes = {}
         for c in range(NCLASS):
             if s.class_launches[c]:

@@ -46,12 +46,19 @@ static long g_tune_emit = 0;       // emit: 0 = binned from 512 Mi bytes, 1 = al
 static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L set
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
+static long g_tune_invpath = 0;    // inverse: 0 = staged single walk (default), 1 = two read-only walks (round 1)
+static long g_tune_invq = 0;       // inverse staged walk: sublists per warp (0 = auto: one full wave of warps)
 static long g_tune_nomark = 0;     // TIMING EXPERIMENT ONLY: inverse first walk without visited marks (wrong output when a cycle has no splitter)
 
 static void apply_device_limits()
 {
     if (g_tune_l2gran == 32 || g_tune_l2gran == 64 || g_tune_l2gran == 128)
         cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g_tune_l2gran);
+    if (getenv("BWTS_B200_TRACE")) {
+        size_t g = 0;
+        cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[trace] cudaLimitMaxL2FetchGranularity = %zu\n", g);
+    }
 }
 
 static bool use_binned_scatter(unsigned n, unsigned kb)
@@ -60,10 +67,11 @@ static bool use_binned_scatter(unsigned n, unsigned kb)
     return g_tune_scatterbin == 2 || n >= (1u << 22);
 }
 
-struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; const char *name = ""; };
+struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; const char *name = ""; int phase = 0; };
 
 struct bwts_b200_ctx {
     int device = 0;
+    int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     u8 *arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
@@ -72,6 +80,7 @@ struct bwts_b200_ctx {
     u32 *h_small = nullptr;  // pinned + mapped, 4 KiB, for counter read-backs
     u32 *h_small_dev = nullptr;  // its device-side address
     int last_cuda = 0;
+    int phase = 0;           // phase the next launches are booked under (stats.phase_ms)
     bool profile = true;
     std::vector<LaunchRec> recs;
     std::vector<cudaEvent_t> pool;
@@ -116,7 +125,7 @@ static cudaEvent_t ctx_event(bwts_b200_ctx *ctx)
         if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); } \
         kern<<<(grid), (block), 0, st>>>(__VA_ARGS__);                               \
         if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
-        ctx->recs.push_back(r__);                                                    \
+        r__.phase = ctx->phase; ctx->recs.push_back(r__);                                                    \
         CK(cudaGetLastError());                                                      \
     } while (0)
 
@@ -127,6 +136,7 @@ static void stats_begin(bwts_b200_ctx *ctx, long len, int direction, cudaStream_
     ctx->stats.direction = direction;
     ctx->recs.clear();
     ctx->pool_used = 0;
+    ctx->phase = 0;
     cudaEventRecord(ctx->ev_begin, st);
 }
 static void stats_end(bwts_b200_ctx *ctx, cudaStream_t st)
@@ -136,6 +146,7 @@ static void stats_end(bwts_b200_ctx *ctx, cudaStream_t st)
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
     ctx->stats.total_ms = ms;
+    ctx->stats.arena_bytes = (long)ctx->arena_bytes;
     ctx->stats.launches = (long)ctx->recs.size();
     static const bool trace = getenv("BWTS_B200_TRACE") != nullptr;  // one line per launch to stderr
     int seq = 0;
@@ -144,7 +155,10 @@ static void stats_end(bwts_b200_ctx *ctx, cudaStream_t st)
         ctx->stats.class_bytes[r.cls] += r.bytes;
         float t = 0;
         if (r.e0 && r.e1) {
-            if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) ctx->stats.class_ms[r.cls] += t;
+            if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+                ctx->stats.class_ms[r.cls] += t;
+                if (r.phase >= 0 && r.phase < BWTS_B200_NPHASE) ctx->stats.phase_ms[r.phase] += t;
+            }
         }
         if (trace)
             fprintf(stderr, "[trace %s n=%ld] %3d %-14s %-24s %9.4f ms %12.0f B %8.1f GB/s\n", ctx->stats.direction ? "inv" : "fwd",
@@ -242,7 +256,7 @@ static int radix_sort(bwts_b200_ctx *ctx, cudaStream_t st, SortBufs &sb, u32 m, 
             sb.k[a], vin, sb.k[b], sb.v[b], m, (u32)(p * RADIX_BITS), sb.hist + p * RADIX_BINS, sb.status,  \
             ctx->epoch);                                                                                  \
         if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
-        ctx->recs.push_back(r__);                                                                         \
+        r__.phase = ctx->phase; ctx->recs.push_back(r__);                                                                         \
         CK(cudaGetLastError());                                                                           \
     } while (0)
         switch (g_tune_onesweep) {
@@ -392,6 +406,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     if (rc) return rc;
 
     CK(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
+    const int PH_SORT0 = 0, PH_ISA = 1, PH_FIX = 2, PH_EMIT = 3;  // bwts_b200_phase_name(0, .)
 
     // Two live sets.  L: groups of any size, sorted by the global radix path (sb, grp, gst).
     // S: groups of at most 32 members, sorted warp-locally (kS, vS, grpS, gstS).
@@ -403,6 +418,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     bool sortedS = false;
     for (;;) {
         // ---- re-rank what was just sorted; S first, L appends to the same S stream
+        ctx->phase = PH_ISA;
         CK(cudaMemsetAsync(rrc, 0, 2 * sizeof(RerankCounters), st));
         LiveOut oS = {vS[cs], grpS[gs ^ 1], gstS[gs ^ 1], nullptr};
         if (mS && sortedS) {
@@ -445,7 +461,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(n, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
                 sb.v[sb.cur], nr_buf, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
             if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
-            ctx->recs.push_back(r__);
+            r__.phase = ctx->phase; ctx->recs.push_back(r__);
             CK(cudaGetLastError());
             LAUNCH(KC_RERANK, 12.0 * n, k_scatter_pairs, cdiv(cdiv(n, 8), 256), 256, bin_pos, bin_val, n, rank);
         }
@@ -506,6 +522,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             break;
         }
         // ---- one doubling round on both live sets
+        ctx->phase = PH_FIX;
+        if (ctx->stats.rounds == 0) ctx->stats.first_live = (long)mS + mL;
         ctx->stats.rounds++;
         ctx->stats.live_sum += (long)mS + mL;
         sortedS = sortedL = false;
@@ -535,7 +553,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                         k_local_sort_cta<true><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
                             sb.v[sb.cur], gst[g], mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
                     if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
-                    ctx->recs.push_back(r__);
+                    r__.phase = ctx->phase; ctx->recs.push_back(r__);
                     CK(cudaGetLastError());
                     sb.cur ^= 1;
                     ctx->stats.cta_rounds++;
@@ -567,6 +585,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     }
 
     // -- emit
+    ctx->phase = PH_EMIT;
+    (void)PH_SORT0;
     if (!linear) {
         const bool emit_binned = g_tune_emit == 2 || (g_tune_emit == 0 && n >= (512u << 20));
         if (emit_binned && kb >= 8) {
@@ -583,7 +603,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(n, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
                 rank, val, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
             if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
-            ctx->recs.push_back(r__);
+            r__.phase = ctx->phase; ctx->recs.push_back(r__);
             CK(cudaGetLastError());
             LAUNCH(KC_EMIT, 9.0 * n, k_scatter_bytes, cdiv(cdiv(n, 4), 256), 256, bin_pos, bin_val, n, d_out);
         } else {
@@ -625,25 +645,29 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     u32 *tilehist = arena_take<u32>(ctx, (size_t)ntiles * 256);
     u32 *chunksum = arena_take<u32>(ctx, (size_t)nchunks * 256);
     u32 *prev = arena_take<u32>(ctx, n);
-    u32 *sid = arena_take<u32>(ctx, n);
+    const bool staged = g_tune_invpath == 0;
+    u32 *sid = staged ? (u32 *)nullptr : arena_take<u32>(ctx, n);  // two-walk path only (sparse element -> sublist map)
     u32 *len_at_min = arena_take<u32>(ctx, n);
     u32 *off = arena_take<u32>(ctx, n);
     uint2 *cyc = arena_take<uint2>(ctx, n);
     u32 *tilecnt = arena_take<u32>(ctx, max(nst, nsc) + 1);
     u32 *small = arena_take<u32>(ctx, 512);  // [0] ns, [2] visited total, [4] unreached, [6] cycles, [8] scan total, [64..320] C
-    if (!tilehist || !chunksum || !prev || !sid || !len_at_min || !off || !cyc || !tilecnt || !small)
+    if (!tilehist || !chunksum || !prev || (!staged && !sid) || !len_at_min || !off || !cyc || !tilecnt || !small)
         return BWTS_B200_EINTERNAL;
     u32 *Ctab = small + 64;
     CK(cudaMemsetAsync(small, 0, 64 * sizeof(u32), st));
 
-    // -- LF map
+    // -- LF map (phases: bwts_b200_phase_name(1, .))
+    ctx->phase = 0;
     LAUNCH(KC_INV_HIST, 1.0 * n, k_inv_tile_hist, ntiles, INV_NT, dB, n, tilehist);
     LAUNCH(KC_INV_SCAN, 1024.0 * ntiles, k_inv_colsum, nchunks, 256, tilehist, ntiles, chunksum);
     LAUNCH(KC_INV_SCAN, 0, k_inv_chunk_scan, 1, 256, chunksum, nchunks, Ctab);
     LAUNCH(KC_INV_SCAN, 2048.0 * ntiles, k_inv_tile_base, nchunks, 256, tilehist, ntiles, chunksum);
+    ctx->phase = 1;
     LAUNCH(KC_INV_LF, 5.0 * n, k_inv_lf_rank, ntiles, INV_NT, dB, n, tilehist, prev);
 
     // -- splitters
+    ctx->phase = 2;
     CK(cudaMemsetAsync(len_at_min, 0, (size_t)n * 4, st));
     LAUNCH(KC_INV_WALK, 0, k_inv_spl_count, nst, 256, n, shift, tilecnt);
     LAUNCH(KC_INV_SCAN, 8.0 * nst, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, nst, small + 0);
@@ -658,15 +682,35 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     uint2 *minfo = arena_take<uint2>(ctx, ns);
     uint4 *srec = arena_take<uint4>(ctx, ns);
     if (!spl || !jm[0] || !jm[1] || !jm[2] || !pv[0] || !pv[1] || !wlen || !minfo || !srec) return BWTS_B200_EINTERNAL;
-    LAUNCH(KC_INV_WALK, 8.0 * ns, k_inv_spl_write, nst, 256, n, shift, tilecnt, spl, sid);
+    u32 *blkoff = nullptr, *nxt = nullptr, *cont = nullptr;
+    u8 *stage = nullptr;
+    if (staged) {
+        blkoff = arena_take<u32>(ctx, (size_t)(n >> 6) + 2);
+        nxt = arena_take<u32>(ctx, ns);
+        cont = arena_take<u32>(ctx, ns);
+        stage = arena_take<u8>(ctx, (size_t)ns * INV_SLOT);
+        if (!blkoff || !nxt || !cont || !stage) return BWTS_B200_EINTERNAL;
+    }
+    LAUNCH(KC_INV_WALK, 8.0 * ns, k_inv_spl_write, nst, 256, n, shift, tilecnt, spl, staged ? (u32 *)nullptr : sid, blkoff);
     // first walk: 4 B read per element, one visited bit set per element (bitmap lives in L2)
     u32 *visited = arena_take<u32>(ctx, (size_t)(n >> 5) + 2);
     if (!visited) return BWTS_B200_EINTERNAL;
     CK(cudaMemsetAsync(visited, 0, ((size_t)(n >> 5) + 2) * 4, st));
-    LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
-           g_tune_nomark ? (u32 *)nullptr : visited, small + 2);
+    if (staged) {
+        // one full wave of warps (64 per SM), each owning a contiguous range of Q sublists
+        const u32 wave = (u32)ctx->sm_count * 64u;
+        u32 Q = g_tune_invq > 0 ? (u32)g_tune_invq : max(64u, cdiv(ns, wave));
+        const u32 nwarps = cdiv(ns, Q);
+        LAUNCH(KC_INV_WALK, 5.0 * n, k_inv_walk_stage, cdiv(nwarps, 8), 256, prev, shift, spl, ns, Q, Ctab, nxt, wlen, minfo,
+               stage, cont, g_tune_nomark ? (u32 *)nullptr : visited, small + 2);
+        LAUNCH(KC_INV_WALK, 20.0 * ns, k_inv_resolve_next, cdiv(ns, 256), 256, nxt, minfo, blkoff, shift, ns, jm[0]);
+    } else {
+        LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
+               g_tune_nomark ? (u32 *)nullptr : visited, small + 2);
+    }
 
     // -- reduced list: cycle minimum, then distance to the sublist holding it
+    ctx->phase = 3;
     const int R = bit_length((u64)ns - 1) + 1;
     const u32 gs = cdiv(ns, 256);
     int cur = 0;
@@ -702,9 +746,15 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     LAUNCH(KC_INV_SCAN, 8.0 * nsc, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, nsc, small + 8);
     LAUNCH(KC_INV_SCAN, 8.0 * n, k_tile_scan_apply_u32, nsc, 256, len_at_min, off, n, tilecnt);
 
-    // -- placement: second walk writes the bytes at descending consecutive positions
+    // -- placement
+    ctx->phase = 4;
     LAUNCH(KC_INV_PLACE, 44.0 * ns, k_inv_spl_record, gs, 256, jmR, pv[pc], cyc, off, ns, srec);
-    LAUNCH(KC_INV_PLACE, 5.0 * n, k_inv_walk_place, cdiv(ns, 128), 128, prev, n, shift, spl, ns, srec, Ctab, d_out);
+    if (staged) {
+        LAUNCH(KC_INV_PLACE, 2.0 * n + 20.0 * ns, k_inv_place_copy, cdiv(ns, 8), 256, stage, wlen, srec, ns, n, d_out);
+        LAUNCH(KC_INV_PLACE, 8.0 * ns, k_inv_walk_tail, cdiv(ns, 128), 128, prev, n, shift, wlen, cont, ns, srec, Ctab, d_out);
+    } else {
+        LAUNCH(KC_INV_PLACE, 5.0 * n, k_inv_walk_place, cdiv(ns, 128), 128, prev, n, shift, spl, ns, srec, Ctab, d_out);
+    }
     if (urec)
         LAUNCH(KC_INV_PLACE, 14.0 * (n - reached), k_inv_place_unreached, cdiv(nwords, 256), 256, dB, n, visited, urec,
                off, d_out);
@@ -746,6 +796,8 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
 #undef OS_ATTR
     bwts_b200_ctx *ctx = new bwts_b200_ctx();
     ctx->device = device;
+    if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count < 1)
+        ctx->sm_count = 148;
     memset(&ctx->stats, 0, sizeof ctx->stats);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc((void **)&ctx->h_small, 4096, cudaHostAllocMapped) != cudaSuccess ||
@@ -797,9 +849,21 @@ static int run_device(bwts_b200_ctx *ctx, int direction, const void *d_in, long 
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->own_stream;
     apply_device_limits();
+    ctx->io_in = nullptr;
+    if ((uintptr_t)d_in & 15) {
+        // the text kernels read 16-byte vectors: an input that is not 16-byte aligned (a slice of a
+        // larger buffer) is first copied to the bottom of the workspace
+        rc = arena_reserve(ctx, workspace_bytes((size_t)len) + 2 * (size_t)len + 1024);
+        if (rc) return rc;
+        ctx->io_bytes = ((size_t)len + 255) & ~(size_t)255;
+        CK(cudaMemcpyAsync(ctx->arena, d_in, (size_t)len, cudaMemcpyDeviceToDevice, st));
+        d_in = ctx->arena;
+        ctx->io_in = ctx->arena;  // tells the cores to skip the I/O region of the arena
+    }
     stats_begin(ctx, len, direction, st);
     rc = direction == 0 ? forward_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, nullptr, FWD_BWTS, st)
                         : inverse_core(ctx, (const u8 *)d_in, (u32)len, (u8 *)d_out, st);
+    ctx->io_in = nullptr;
     if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
     stats_end(ctx, st);
     cudaError_t e = cudaGetLastError();
@@ -1044,6 +1108,10 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
         ctx->pipe_ring_out = new PinnedRing();
         rc = ctx->pipe_ring_out->init();
     }
+    if (rc) {  // a half-built pipeline must not survive into the next call
+        pipe_state_destroy(ctx);
+        return rc;
+    }
     u8 *d_io = ctx->pipe_io;
     cudaStream_t s_in = ctx->pipe_s_in, s_out = ctx->pipe_s_out;
     cudaEvent_t *ev_loaded = ctx->pipe_ev_loaded;
@@ -1195,6 +1263,14 @@ extern "C" const char *bwts_b200_class_name(int cls)
 {
     return (cls >= 0 && cls < BWTS_B200_NCLASS) ? kclass_names[cls] : nullptr;
 }
+extern "C" const char *bwts_b200_phase_name(int direction, int phase)
+{
+    static const char *fwd[] = {"Suffix sort", "Compute ISA", "Fix sort order", "Generate BWTS"};
+    static const char *inv[] = {"Count bytes", "LF map", "Walk sublists", "Rank sublists", "Place bytes"};
+    if (phase < 0) return nullptr;
+    if (direction == 0) return phase < 4 ? fwd[phase] : nullptr;
+    return phase < 5 ? inv[phase] : nullptr;
+}
 extern "C" int bwts_b200_set_profile(bwts_b200_ctx *ctx, int on)
 {
     if (!ctx) return BWTS_B200_EINVAL;
@@ -1242,5 +1318,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 9) { g_tune_emit = value; return 0; }
     if (key == 10) { g_tune_l2gran = value; return 0; }
     if (key == 11) { g_tune_nomark = value; return 0; }
+    if (key == 12) { g_tune_invpath = value; return 0; }
+    if (key == 13) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invq = value; return 0; }
     return BWTS_B200_EINVAL;
 }

@@ -188,8 +188,12 @@ __global__ void __launch_bounds__(256) k_inv_spl_count(u32 n, u32 shift, u32 *__
         tilecnt[blockIdx.x] = s;
     }
 }
+// sid (two-walk path): sparse map element -> sublist id, written at splitter slots only.
+// blkoff (staged path): blkoff[b] = number of splitters below element 64 b; the id of the sublist
+// that starts at splitter p is blkoff[p >> 6] + the splitters in [p & ~63, p) (sid_of).
 __global__ void __launch_bounds__(256) k_inv_spl_write(u32 n, u32 shift, const u32 *__restrict__ tileoff,
-                                                       u32 *__restrict__ spl, u32 *__restrict__ sid)
+                                                       u32 *__restrict__ spl, u32 *__restrict__ sid,
+                                                       u32 *__restrict__ blkoff)
 {
     __shared__ u32 ws[8];
     const u32 base = blockIdx.x * SP_TILE + threadIdx.x * 16;
@@ -201,13 +205,20 @@ __global__ void __launch_bounds__(256) k_inv_spl_write(u32 n, u32 shift, const u
     __syncthreads();
     u32 s = tileoff[blockIdx.x] + incl - c;
     for (u32 w = 0; w < (threadIdx.x >> 5); w++) s += ws[w];
+    if (blkoff && (threadIdx.x & 3) == 0 && base < n) blkoff[base >> 6] = s;  // SP_TILE and 16 divide 64-blocks evenly
 #pragma unroll
     for (int q = 0; q < 16; q++)
         if ((base + q < n) && is_splitter(base + q, shift)) {
             spl[s] = base + q;
-            sid[base + q] = s;  // sparse: only splitter slots of sid are ever written or read
+            if (sid) sid[base + q] = s;
             s++;
         }
+}
+static __device__ __forceinline__ u32 sid_of(const u32 *__restrict__ blkoff, u32 p, u32 shift)
+{
+    u32 s = __ldg(blkoff + (p >> 6));
+    for (u32 q = p & ~63u; q < p; q++) s += is_splitter(q, shift);
+    return s;
 }
 
 // first walk: one thread per splitter follows prev until the next splitter.  (A persistent
@@ -384,3 +395,152 @@ __global__ void __launch_bounds__(256) k_inv_spl_record(const u64 *__restrict__ 
     srec[s] = make_uint4(A, L, off[cm], 0u);
 }
 
+
+// ---- staged single walk (default path) ----------------------------------------------------------
+// The two-walk form above chases every element twice (ncu, round 1: 89 B of DRAM traffic per
+// 4-byte step, 22x the algorithmic bytes, lanes idle 3/4 of the time because a warp runs until its
+// longest sublist ends).  Here the first walk already recovers the bytes: the byte of element i is
+// the c with C[c] <= prev[i] < C[c+1], and the walker of sublist s parks it at stage[s][offset]
+// (INV_SLOT bytes per sublist, written as full 32-byte sectors).  After the list ranking a
+// streaming kernel copies every slot to its place in the output (a sublist is at most two
+// descending runs there); only the 1.8 % of the elements beyond offset INV_SLOT of their sublist
+// are chased a second time, from the element the first walk parked in cont[s].
+// Lanes are refilled: warp w owns the sublists [w Q, (w+1) Q) and a lane whose sublist ended takes
+// the next one of the warp's range (ballot + popc, no atomics), so the warp stays full until its
+// range runs dry.
+#define INV_SLOT 256
+
+static __device__ __forceinline__ u32 byte_of_rank(const u32 *sC, u32 p)
+{
+    u32 c = 0;  // largest c with C[c] <= p
+#pragma unroll
+    for (u32 step = 128; step > 0; step >>= 1)
+        if (sC[c + step] <= p) c += step;
+    return c;
+}
+
+__global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ prev, u32 shift,
+                                                        const u32 *__restrict__ spl, u32 ns, u32 Q,
+                                                        const u32 *__restrict__ Ctab, u32 *__restrict__ nxt,
+                                                        u32 *__restrict__ wlen, uint2 *__restrict__ minfo,
+                                                        u8 *__restrict__ stage, u32 *__restrict__ cont,
+                                                        u32 *__restrict__ visited, u32 *__restrict__ total)
+{
+    __shared__ u32 sC[257];
+    for (u32 t = threadIdx.x; t < 257; t += blockDim.x) sC[t] = Ctab[t];
+    __syncthreads();
+    const u32 lane = lane_id(), lt = lanemask_lt();
+    const u64 lo64 = ((u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * Q;
+    if (lo64 >= ns) return;  // warp-uniform
+    u32 next = (u32)lo64;
+    const u32 hi = (u32)min((u64)ns, lo64 + Q);
+    u32 s = NONE32, i = 0, o = 0, mn = 0, mo = 0, sum = 0;
+    u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // 32 staged bytes
+    for (;;) {
+        const u32 idle = __ballot_sync(FULL_MASK, s == NONE32);
+        if (idle) {
+            if (s == NONE32) {
+                const u32 cand = next + __popc(idle & lt);
+                if (cand < hi) {
+                    s = cand;
+                    i = __ldg(spl + s);
+                    o = 0; mn = i; mo = 0;
+                    a0 = a1 = a2 = a3 = 0;
+                }
+            }
+            next += __popc(idle);
+            if (__all_sync(FULL_MASK, s == NONE32)) break;
+        }
+        if (s != NONE32) {
+            const u32 p = ldg_stream_u32(prev + i);
+            if (visited) atomicOr(visited + (i >> 5), 1u << (i & 31));
+            if (o < INV_SLOT) {
+                const u32 c = byte_of_rank(sC, p);
+                const u32 b = o & 31, q = b >> 3;
+                const u64 v = (u64)c << (8 * (b & 7));
+                a0 |= (q == 0) ? v : 0ull;
+                a1 |= (q == 1) ? v : 0ull;
+                a2 |= (q == 2) ? v : 0ull;
+                a3 |= (q == 3) ? v : 0ull;
+                if (b == 31) {
+                    uint4 *dst = (uint4 *)(stage + (u64)s * INV_SLOT + (o & ~31u));
+                    dst[0] = make_uint4((u32)a0, (u32)(a0 >> 32), (u32)a1, (u32)(a1 >> 32));
+                    dst[1] = make_uint4((u32)a2, (u32)(a2 >> 32), (u32)a3, (u32)(a3 >> 32));
+                    a0 = a1 = a2 = a3 = 0;
+                }
+            } else if (o == INV_SLOT) {
+                cont[s] = i;  // the element at offset INV_SLOT: where k_inv_walk_tail resumes
+            }
+            o++;
+            if (is_splitter(p, shift)) {
+                if (o <= INV_SLOT && (o & 31)) {
+                    uint4 *dst = (uint4 *)(stage + (u64)s * INV_SLOT + ((o - 1) & ~31u));
+                    dst[0] = make_uint4((u32)a0, (u32)(a0 >> 32), (u32)a1, (u32)(a1 >> 32));
+                    dst[1] = make_uint4((u32)a2, (u32)(a2 >> 32), (u32)a3, (u32)(a3 >> 32));
+                }
+                nxt[s] = p;  // the splitter that starts the next sublist (resolved to its id afterwards)
+                wlen[s] = o;
+                minfo[s] = make_uint2(mn, mo);
+                sum += o;
+                s = NONE32;
+            } else {
+                i = p;
+                if (p < mn) { mn = p; mo = o; }
+            }
+        }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0 && sum) atomicAdd(total, sum);
+}
+
+// jm[s] = id of the next sublist << 32 | smallest index of sublist s
+__global__ void __launch_bounds__(256) k_inv_resolve_next(const u32 *__restrict__ nxt, const uint2 *__restrict__ minfo,
+                                                          const u32 *__restrict__ blkoff, u32 shift, u32 ns,
+                                                          u64 *__restrict__ jm)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    jm[s] = ((u64)sid_of(blkoff, nxt[s], shift) << 32) | (u64)minfo[s].x;
+}
+
+// one warp per sublist: its staged bytes go to out[top - d], d = (A + offset) mod L
+__global__ void __launch_bounds__(256) k_inv_place_copy(const u8 *__restrict__ stage, const u32 *__restrict__ wlen,
+                                                        const uint4 *__restrict__ srec, u32 ns, u32 n,
+                                                        u8 *__restrict__ out)
+{
+    const u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= ns) return;
+    const u32 len = min(__ldg(wlen + s), (u32)INV_SLOT);
+    const uint4 r = __ldg(srec + s);
+    const u32 L = r.y, top = n - 1 - r.z;
+    const u8 *src = stage + s * INV_SLOT;
+    for (u32 o = lane_id(); o < len; o += 32) {
+        u32 d = r.x + o;  // A < L and o < len <= L
+        if (d >= L) d -= L;
+        out[top - d] = src[o];
+    }
+}
+
+// the elements beyond offset INV_SLOT of their sublist: a second walk from cont[s]
+__global__ void __launch_bounds__(128) k_inv_walk_tail(const u32 *__restrict__ prev, u32 n, u32 shift,
+                                                       const u32 *__restrict__ wlen, const u32 *__restrict__ cont,
+                                                       u32 ns, const uint4 *__restrict__ srec,
+                                                       const u32 *__restrict__ Ctab, u8 *__restrict__ out)
+{
+    __shared__ u32 sC[257];
+    for (u32 t = threadIdx.x; t < 257; t += blockDim.x) sC[t] = Ctab[t];
+    __syncthreads();
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns || wlen[s] <= INV_SLOT) return;
+    const uint4 r = srec[s];
+    const u32 L = r.y, top = n - 1 - r.z;
+    u32 d = r.x + INV_SLOT;  // < 2 L
+    if (d >= L) d -= L;
+    u32 i = cont[s];
+    do {
+        const u32 p = ldg_stream_u32(prev + i);
+        out[top - d] = (u8)byte_of_rank(sC, p);
+        if (++d == L) d = 0;
+        i = p;
+    } while (!is_splitter(i, shift));
+}

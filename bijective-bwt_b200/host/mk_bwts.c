@@ -25,6 +25,6 @@ int main(int argc, char **argv)
 		perror(outname);
 		exit(1);
 	}
-	fwrite(bwts, 1, (size_t)len, fp);
+	write_output(bwts, len, fp, "Write BWTS");
 	return 0;
 }

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/bwts_b200.h"
 
@@ -20,15 +21,43 @@ static long env_long(const char *name, long dflt)
 	return (v && *v) ? atol(v) : dflt;
 }
 
+/* BWTS_B200_TIMINGS=1: the reference's `<label> time <seconds>` lines (-DSHOW_TIMINGS,
+ * /root/reference/mk_bwts_sa.c:13-22) in the reference's order -- Suffix sort (:50), Compute ISA
+ * (:124), Fix sort order (:168), Generate BWTS (:190); the tool adds Write BWTS (:62) after its
+ * fwrite -- booked from CUDA-event times of the kernels of each phase, then one line of per-transform
+ * diagnostics, the counterpart of /root/reference/mk_bwts_new_algo.c:127, then the kernel classes. */
 static void print_timings(bwts_b200_ctx *ctx)
 {
 	bwts_b200_stats s;
 	if (bwts_b200_get_stats(ctx, &s) != 0) return;
+	for (int p = 0; p < BWTS_B200_NPHASE; p++) {
+		const char *name = bwts_b200_phase_name(s.direction, p);
+		if (name) fprintf(stderr, "%s time %0.3f\n", name, s.phase_ms[p] / 1000.0);
+	}
+	if (s.direction == 0)
+		fprintf(stderr, "Factors: %10ld; longest: %10ld; alphabet bits: %d; initial depth: %d; live after initial sort: %10ld; "
+		        "doubling rounds: %d (warp-local %d, CTA-local %d); radix passes: %d; live sum: %ld; workspace bytes/byte: %.1f\n",
+		        s.factors, s.longest_factor, s.alphabet_bits, s.initial_depth, s.first_live, s.rounds, s.local_rounds,
+		        s.cta_rounds, s.radix_passes, s.live_sum, s.len ? (double)s.arena_bytes / (double)s.len : 0.0);
+	else
+		fprintf(stderr, "Cycles: %10ld; sublists: %10ld; unreached: %10ld; workspace bytes/byte: %.1f\n", s.factors,
+		        s.splitters, s.unreached, s.len ? (double)s.arena_bytes / (double)s.len : 0.0);
 	for (int c = 0; c < BWTS_B200_NCLASS; c++)
 		if (s.class_launches[c])
-			fprintf(stderr, "%s time %0.3f (%ld launches)\n", bwts_b200_class_name(c),
+			fprintf(stderr, "  class %s time %0.6f (%ld launches)\n", bwts_b200_class_name(c),
 			        s.class_ms[c] / 1000.0, s.class_launches[c]);
-	fprintf(stderr, "Transform time %0.3f\n", s.total_ms / 1000.0);
+	fprintf(stderr, "Transform time %0.3f (H2D %0.3f, D2H %0.3f)\n", s.total_ms / 1000.0, s.h2d_ms / 1000.0, s.d2h_ms / 1000.0);
+}
+
+/* fwrite with the reference's last mark: "Write BWTS time" (/root/reference/mk_bwts_sa.c:60-62) */
+static void write_output(const unsigned char *data, long len, FILE *fp, const char *label)
+{
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	fwrite(data, 1, (size_t)len, fp);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	if (env_long("BWTS_B200_TIMINGS", 0))
+		fprintf(stderr, "%s time %0.3f\n", label, (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
 }
 
 /* direction 0 = forward, 1 = inverse.  Exits with the reference's convention on failure. */

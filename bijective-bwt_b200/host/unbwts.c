@@ -29,7 +29,7 @@ static void write_out(const unsigned char *data, long n, char *out_arg, char *in
 		perror(name);
 		exit(1);
 	}
-	fwrite(data, 1, (size_t)n, fp);
+	write_output(data, n, fp, "Write text");
 	fclose(fp);
 }
 

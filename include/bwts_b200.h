@@ -89,6 +89,7 @@ int bwts_b200_inverse_device(bwts_b200_ctx *ctx, const void *d_in, long len, voi
 /* ---- introspection --------------------------------------------------------------- */
 
 #define BWTS_B200_NCLASS 16
+#define BWTS_B200_NPHASE 8
 typedef struct {
     long   len;                 /* length of the last transform                         */
     int    direction;           /* 0 forward, 1 inverse                                 */
@@ -114,10 +115,19 @@ typedef struct {
     double h2d_ms;
     double d2h_ms;
     int    lyndon_fallback;     /* forward: 1 if the Lyndon boundaries came from the suffix-sort fallback */
+    /* device time per phase, the counterpart of the reference's MARK_TIME marks
+     * (/root/reference/mk_bwts_sa.c:13-22,50,124,168,190); names: bwts_b200_phase_name       */
+    double phase_ms[BWTS_B200_NPHASE];
+    long   arena_bytes;         /* device workspace held by the context after this transform */
+    long   first_live;          /* forward: rotations still tied after the initial sort      */
 } bwts_b200_stats;
 
 int bwts_b200_get_stats(const bwts_b200_ctx *ctx, bwts_b200_stats *out);
 const char *bwts_b200_class_name(int cls);          /* NULL when cls is out of range   */
+/* forward (direction 0): "Suffix sort", "Compute ISA", "Fix sort order", "Generate BWTS" -- the
+ * reference's own labels, in its order; inverse (direction 1): "Count bytes", "LF map",
+ * "Walk sublists", "Rank sublists", "Place bytes".  NULL past the last phase.           */
+const char *bwts_b200_phase_name(int direction, int phase);
 int bwts_b200_set_profile(bwts_b200_ctx *ctx, int on);   /* per-launch events (default on) */
 
 const char *bwts_b200_strerror(int code);

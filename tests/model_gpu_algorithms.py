@@ -278,6 +278,177 @@ def inverse(Bs, shift=26):
     return out.tobytes()
 
 
+def inverse_staged(Bs, shift=26, slot=256, Q=64):
+    """inverse.cuh, staged path: k_inv_spl_write (blkoff) -> k_inv_walk_stage (warps of 32 lanes with
+    lane refill over a range of Q sublists, bytes parked in 32-byte sectors of a slot, cont[] at
+    offset `slot`) -> k_inv_resolve_next (sid_of) -> list ranking as before -> k_inv_place_copy +
+    k_inv_walk_tail.  Mirrors the CUDA control flow statement by statement."""
+    B = np.frombuffer(bytes(Bs), dtype=np.uint8)
+    n = len(B)
+    cnt = np.bincount(B, minlength=256)
+    C = np.concatenate((np.cumsum(cnt) - cnt, [n]))  # C[256] = n
+
+    def byte_of_rank(p):
+        c, step = 0, 128
+        while step:
+            if C[c + step] <= p:
+                c += step
+            step >>= 1
+        return c
+
+    prev = np.zeros(n, dtype=np.int64)
+    seen = np.zeros(256, dtype=np.int64)
+    for i in range(n):
+        prev[i] = C[B[i]] + seen[B[i]]
+        seen[B[i]] += 1
+    spl = [i for i in range(n) if is_splitter(i, shift)]
+    ns = len(spl)
+    blkoff = np.zeros((n >> 6) + 2, dtype=np.int64)
+    run = 0
+    for i in range(n):
+        if i % 64 == 0:
+            blkoff[i >> 6] = run
+        run += bool(is_splitter(i, shift))
+
+    def sid_of(p):
+        s = blkoff[p >> 6]
+        for q in range(p & ~63, p):
+            s += bool(is_splitter(q, shift))
+        return int(s)
+
+    stage = np.full(ns * slot, 0xEE, dtype=np.uint8)  # poison: unwritten bytes must never be placed
+    nxt = np.zeros(ns, dtype=np.int64)
+    wlen = np.zeros(ns, dtype=np.int64)
+    mnv = np.zeros(ns, dtype=np.int64)
+    mno = np.zeros(ns, dtype=np.int64)
+    cont = np.full(ns, -1, dtype=np.int64)
+    visited = np.zeros(n, dtype=bool)
+    total = 0
+    NONE = -1
+    nwarps = (ns + Q - 1) // Q
+    for w in range(nwarps):
+        nxt_s, hi = w * Q, min(ns, (w + 1) * Q)
+        st = [dict(s=NONE) for _ in range(32)]
+        while True:
+            idle = [l for l in range(32) if st[l]["s"] == NONE]
+            if idle:
+                for r, l in enumerate(idle):
+                    cand = nxt_s + r
+                    if cand < hi:
+                        st[l] = dict(s=cand, i=spl[cand], o=0, mn=spl[cand], mo=0, acc=bytearray(32))
+                nxt_s += len(idle)
+                if all(x["s"] == NONE for x in st):
+                    break
+            for x in st:
+                if x["s"] == NONE:
+                    continue
+                s_, i, o = x["s"], x["i"], x["o"]
+                p = int(prev[i])
+                visited[i] = True
+                if o < slot:
+                    b = o & 31
+                    x["acc"][b] = byte_of_rank(p)
+                    if b == 31:
+                        base = s_ * slot + (o & ~31)
+                        stage[base:base + 32] = np.frombuffer(bytes(x["acc"]), np.uint8)
+                        x["acc"] = bytearray(32)
+                elif o == slot:
+                    cont[s_] = i
+                o += 1
+                x["o"] = o
+                if is_splitter(p, shift):
+                    if o <= slot and (o & 31):
+                        base = s_ * slot + ((o - 1) & ~31)
+                        stage[base:base + 32] = np.frombuffer(bytes(x["acc"]), np.uint8)
+                    nxt[s_], wlen[s_], mnv[s_], mno[s_] = p, o, x["mn"], x["mo"]
+                    total += o
+                    x["s"] = NONE
+                else:
+                    x["i"] = p
+                    if p < x["mn"]:
+                        x["mn"], x["mo"] = p, o
+    nxt = np.array([sid_of(int(p)) for p in nxt], dtype=np.int64)
+    w_ = wlen
+    # reduced list: identical to inverse()
+    jmp, cm = nxt.copy(), mnv.copy()
+    r = 0
+    while (1 << r) < max(ns, 1):
+        cm = np.minimum(cm, cm[jmp]) if ns else cm
+        jmp = jmp[jmp] if ns else jmp
+        r += 1
+    if ns:
+        cm = np.minimum(cm, cm[jmp])
+    origin = mnv == cm
+    ptr = np.where(origin[nxt], -1, nxt) if ns else nxt
+    val = w_.copy()
+    for _ in range(r + 1):
+        has = ptr >= 0
+        val = np.where(has, val + val[np.where(has, ptr, 0)], val)
+        ptr = np.where(has, ptr[np.where(has, ptr, 0)], -1)
+    D = val
+    lenAtMin = np.zeros(n, dtype=np.int64)
+    cycL = np.zeros(n, dtype=np.int64)
+    cycO = np.zeros(n, dtype=np.int64)
+    for s_ in range(ns):
+        if origin[s_]:
+            lenAtMin[cm[s_]] = D[s_]
+            cycL[cm[s_]] = D[s_]
+            cycO[cm[s_]] = mno[s_]
+    direct = np.zeros(n, dtype=bool)
+    dir_m = np.zeros(n, dtype=np.int64)
+    dir_d = np.zeros(n, dtype=np.int64)
+    if total != n:
+        for i in range(n):
+            if not visited[i]:
+                j, steps, mn, mstep = prev[i], 1, i, 0
+                while j != i:
+                    if j < mn:
+                        mn, mstep = j, steps
+                    j = prev[j]
+                    steps += 1
+                direct[i] = True
+                dir_m[i], dir_d[i] = mn, (steps - mstep) % steps
+                if mn == i:
+                    lenAtMin[i] = steps
+    off = np.cumsum(lenAtMin) - lenAtMin
+    out = np.full(n, 0xDD, dtype=np.uint8)
+    written = np.zeros(n, dtype=np.int64)
+    for s_ in range(ns):
+        L = int(cycL[cm[s_]])
+        A = int((L - D[s_] - cycO[cm[s_]]) % L)
+        top = n - 1 - int(off[cm[s_]])
+        # k_inv_place_copy
+        for o in range(min(int(wlen[s_]), slot)):
+            d = A + o
+            if d >= L:
+                d -= L
+            out[top - d] = stage[s_ * slot + o]
+            written[top - d] += 1
+        # k_inv_walk_tail
+        if wlen[s_] > slot:
+            d = A + slot
+            if d >= L:
+                d -= L
+            i = int(cont[s_])
+            while True:
+                p = int(prev[i])
+                out[top - d] = byte_of_rank(p)
+                written[top - d] += 1
+                d += 1
+                if d == L:
+                    d = 0
+                i = p
+                if is_splitter(i, shift):
+                    break
+    for i in range(n):
+        if direct[i]:
+            pos = n - 1 - off[dir_m[i]] - dir_d[i]
+            out[pos] = B[i]
+            written[pos] += 1
+    assert (written == 1).all(), "every output byte is written exactly once"
+    return out.tobytes()
+
+
 # ---- models of the round-1b kernels --------------------------------------------------------------
 
 def owned_ranges(gst, T):

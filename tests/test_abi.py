@@ -117,3 +117,14 @@ def test_stats_struct_layout_matches_the_header(tmp_path):
     csize = int(subprocess.check_output([str(exe)]).decode())
     bwts = helpers.load_product()
     assert csize == ctypes.sizeof(bwts.Stats)
+
+
+def test_phase_names_are_the_reference_marks(bwts):
+    """bwts_b200_phase_name: forward phases carry the labels of the reference's MARK_TIME calls
+    (/root/reference/mk_bwts_sa.c:50,124,168,190) in the reference's order"""
+    L = bwts.lib()
+    fwd = [L.bwts_b200_phase_name(0, i) for i in range(bwts.NPHASE)]
+    assert [f.decode() for f in fwd if f] == ["Suffix sort", "Compute ISA", "Fix sort order", "Generate BWTS"]
+    inv = [L.bwts_b200_phase_name(1, i) for i in range(bwts.NPHASE)]
+    assert [f.decode() for f in inv if f] == ["Count bytes", "LF map", "Walk sublists", "Rank sublists", "Place bytes"]
+    assert L.bwts_b200_phase_name(0, -1) is None and L.bwts_b200_phase_name(1, 99) is None

@@ -167,15 +167,59 @@ def test_oracle_sample_16mib(ctx, oracle, gen):
 
 
 def test_blocks_equal_concatenated_single_blocks(bwts, oracle, gen):
+    """the in-process dealer (run_blocks: one host thread, context and pipeline per device) over ALL
+    devices of the box, ragged last block, against the per-block oracle output"""
     x = gen.make("text", 21, 3_000_000)
     b = 1 << 20
     want = b"".join(oracle.forward(x[o:o + b]) for o in range(0, len(x), b))
-    ndev = min(2, bwts.device_count())
-    got = bwts.forward_blocks(x, b, devices=list(range(ndev)))
-    assert got == want
-    assert bwts.inverse_blocks(got, b, devices=list(range(ndev))) == x
+    ndev = bwts.device_count()
+    devs = list(range(ndev))
+    got = bwts.forward_blocks(x, b, devices=devs)
+    assert got == want, f"forward_blocks over {ndev} device(s)"
+    assert bwts.inverse_blocks(got, b, devices=devs) == x, f"inverse_blocks over {ndev} device(s)"
     # block_len <= 0 means the reference's behaviour: one block
     assert bwts.forward_blocks(x, 0) == oracle.forward(x)
+
+
+def test_dealer_needs_two_devices(bwts, oracle, gen):
+    """the multi-device path proper: more blocks than devices, ragged tail, every device used, device
+    lists in both orders.  Skipped (explicitly, not silently narrowed) on a one-GPU box."""
+    ndev = bwts.device_count()
+    if ndev < 2:
+        pytest.skip(f"needs >= 2 CUDA devices, this box has {ndev}")
+    x = gen.make("dna", 22, 7 * (1 << 20) + 4321)
+    b = 1 << 20
+    want = b"".join(oracle.forward(x[o:o + b]) for o in range(0, len(x), b))
+    for devs in (list(range(ndev)), list(range(ndev))[::-1], [1, 0]):
+        got = bwts.forward_blocks(x, b, devices=devs)
+        assert got == want, f"forward_blocks, devices {devs}"
+        assert bwts.inverse_blocks(got, b, devices=devs) == x, f"inverse_blocks, devices {devs}"
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_full_size_c5_blocks(bwts, gen, block):
+    """BASELINE configs[4]: each of the eight 256 MiB blocks of the multi-block file (seeds 50..57),
+    SHA-256 of the forward output == the unmodified reference's, and the round trip"""
+    gold = FULLSIZE[f"C5_{block}"]
+    x = gen.make(gold["kind"], gold["seed"], gold["n"])
+    assert helpers.sha256(x) == gold["input_sha256"]
+    with bwts.Context(0) as c:
+        y = c.forward_host(x)
+        assert helpers.sha256(y) == gold["fwd_sha256"], "differs from the reference's mk_bwts output"
+        assert c.inverse_host(y) == x
+
+
+def test_full_size_fibonacci_256mib(bwts, gen):
+    """SURVEY 8(d)'s stress variant of configs[2]: the 256 MiB Fibonacci word"""
+    if "C3F" not in FULLSIZE:
+        pytest.skip("tests/golden/fullsize.json has no C3F entry (the reference run did not finish)")
+    gold = FULLSIZE["C3F"]
+    x = gen.make(gold["kind"], gold["seed"], gold["n"])
+    assert helpers.sha256(x) == gold["input_sha256"]
+    with bwts.Context(0) as c:
+        y = c.forward_host(x)
+        assert helpers.sha256(y) == gold["fwd_sha256"], "differs from the reference's mk_bwts output"
+        assert c.inverse_host(y) == x
 
 
 def test_onesweep_tile_shapes(bwts, ctx, oracle, gen):
@@ -324,6 +368,28 @@ def test_device_resident_api_with_torch(bwts, ctx, oracle, gen):
     assert st["launches"] > 0 and st["direction"] == 1
 
 
+def test_device_api_accepts_unaligned_input(bwts, ctx, oracle, gen):
+    """d_in at every offset 1..15 from a 16-byte boundary (a slice of a larger tensor): the text kernels
+    read 16-byte vectors, the library must realign instead of faulting"""
+    import torch
+    dev = torch.device("cuda:0")
+    x = gen.make("text", 33, 300_001)
+    big = torch.zeros(len(x) + 64, dtype=torch.uint8, device=dev)
+    out = torch.zeros(len(x) + 64, dtype=torch.uint8, device=dev)
+    want_f, want_i = oracle.forward(x), oracle.inverse(x)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for off in (1, 2, 3, 5, 8, 13, 15):
+        view = big[off:off + len(x)]
+        view.copy_(torch.frombuffer(bytearray(x), dtype=torch.uint8))
+        o = out[(off * 7) % 16:(off * 7) % 16 + len(x)]
+        ctx.forward_device(view.data_ptr(), len(x), o.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert bytes(o.cpu().numpy()) == want_f, off
+        ctx.inverse_device(view.data_ptr(), len(x), o.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert bytes(o.cpu().numpy()) == want_i, off
+
+
 def test_suffix_array_seam(bwts, oracle, gen):
     for x in (b"banana", b"mississippi", b"a" * 1000, gen.make("text", 5, 200_000), gen.make("dna", 6, 300_000),
               helpers.fibonacci_word(50_000)):
@@ -350,6 +416,48 @@ def test_cli_tools_match_reference_layout(oracle, gen, tmp_path):
     env = dict(os.environ, BWTS_B200_BLOCK="131072")
     out = subprocess.run([str(bindir / "mk_bwts"), str(src)], capture_output=True, check=True, env=env).stdout
     assert out == b"".join(oracle.forward(x[o:o + 131072]) for o in range(0, len(x), 131072))
+
+
+def test_timings_use_the_reference_phase_labels(gen, tmp_path):
+    """BWTS_B200_TIMINGS=1 prints the reference's `<label> time <seconds>` lines
+    (-DSHOW_TIMINGS, /root/reference/mk_bwts_sa.c:13-22,50,62,124,168,190) with the reference's labels in the
+    reference's order -- compared with what the unmodified timed reference binary prints for the same
+    file -- then one line of per-transform diagnostics (mk_bwts_new_algo.c:127's counterpart)."""
+    import re
+    bindir = helpers.PKG / "bin"
+    x = gen.make("dna", 77, 700_000)
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.write_bytes(x)
+    env = dict(os.environ, BWTS_B200_TIMINGS="1")
+    p = subprocess.run([str(bindir / "mk_bwts"), str(src), str(dst)], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    pat = re.compile(r"^([A-Z][A-Za-z ]+) time (\d+\.\d{3})$")
+    labels = [m.group(1) for m in (pat.match(ln) for ln in p.stderr.splitlines()) if m]
+    want = ["Suffix sort", "Compute ISA", "Fix sort order", "Generate BWTS", "Write BWTS"]
+    ref_timed = helpers.REF_DIR / "mk_bwts_timed"
+    if ref_timed.exists():
+        r = subprocess.run([str(ref_timed), str(src), str(tmp_path / "ref_out")], capture_output=True, text=True)
+        assert r.returncode == 0
+        ref_labels = [m.group(1) for m in (pat.match(ln) for ln in r.stderr.splitlines()) if m]
+        assert ref_labels == want, "the reference's own marks"
+        assert (tmp_path / "ref_out").read_bytes() == dst.read_bytes()
+    assert [l for l in labels if l in want] == want, p.stderr
+    diag = [ln for ln in p.stderr.splitlines() if ln.startswith("Factors:")]
+    assert len(diag) == 1
+    m = re.match(r"Factors:\s+(\d+); longest:\s+(\d+); alphabet bits: (\d+); initial depth: (\d+); "
+                 r"live after initial sort:\s+(\d+); doubling rounds: (\d+) \(warp-local (\d+), CTA-local (\d+)\); "
+                 r"radix passes: (\d+); live sum: (\d+); workspace bytes/byte: ([0-9.]+)$", diag[0])
+    assert m, diag[0]
+    factors, longest, bits, depth, live0, rounds = (int(m.group(i)) for i in range(1, 7))
+    assert factors >= 1 and 1 <= longest <= len(x) and bits == 2 and depth == 32 and rounds >= 1 and live0 <= len(x)
+    assert int(m.group(10)) >= live0 > 0
+    # the inverse tool: additive labels, same format
+    p = subprocess.run([str(bindir / "unbwts"), str(dst), str(tmp_path / "back")], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    labels = [m.group(1) for m in (pat.match(ln) for ln in p.stderr.splitlines()) if m]
+    assert [l for l in labels if l != "Transform"] == ["Count bytes", "LF map", "Walk sublists", "Rank sublists", "Place bytes", "Write text"], p.stderr
+    assert re.search(r"^Cycles:\s+%d; sublists:\s+\d+; unreached:\s+\d+;" % factors, p.stderr, re.M), p.stderr
+    assert (tmp_path / "back").read_bytes() == x
 
 
 def test_context_reuse_across_sizes(ctx, oracle, gen):

@@ -37,6 +37,21 @@ def test_splitter_inverse(oracle):
             assert model.inverse(x, shift=shift) == oracle.inverse(x), (name, shift)
 
 
+def test_staged_inverse(oracle):
+    """the staged single-walk inverse: small slots and warp ranges so that few-byte inputs overflow
+    their slots (cont[] + tail walk), flush partial sectors and refill lanes"""
+    rng = np.random.default_rng(5)
+    cases = _cases()
+    for n in (300, 700, 1500):
+        cases.append((f"rnd2_{n}", rng.integers(0, 2, size=n, dtype=np.uint8).tobytes()))
+        cases.append((f"rnd256_{n}", rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()))
+        cases.append((f"fwd_text_{n}", oracle.forward(bytes(rng.integers(97, 101, size=n, dtype=np.uint8)))))
+    for name, x in cases:
+        want = oracle.inverse(x)
+        for shift, slot, Q in ((30, 32, 2), (28, 32, 3), (31, 64, 1), (27, 32, 5), (26, 32, 4), (25, 64, 7), (27, 96, 40), (26, 256, 64)):
+            assert model.inverse_staged(x, shift=shift, slot=slot, Q=Q) == want, (name, shift, slot, Q)
+
+
 def test_ownership_rule_partitions_groups():
     """every group is owned by exactly one worker, and a worker's share is < 2T slots when no
     group has more than T members (k_local_sort_warp: T = 32, k_local_sort_cta: T = 4096)"""
