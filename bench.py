@@ -311,6 +311,32 @@ def run_reference_arm(args, rank, world):
 
 # --------------------------------------------------------------------------- GPU arm
 
+def pin_to_gpu_numa_node(torch, local_rank):
+    """Best effort: run this rank's host threads (and so its pinned allocations, first touch) on the
+    NUMA node the GPU hangs off.  Returns what was found for the JSON line."""
+    info = {"node": None, "cpus": None, "pinned": False}
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        cpulist = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        info["cpus"] = len(cpus)
+        if cpus and cpus != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, cpus)
+            info["pinned"] = True
+    except Exception as e:  # containers often hide the topology
+        info["error"] = type(e).__name__
+    return info
+
+
 class Blocks:
     """the blocks one rank owns: host (pinned) and device buffers, golden names"""
 
@@ -398,7 +424,9 @@ def device_resident(torch, ctx, blocks, stream, flush, steps, warmup, golden, ag
 
 def host_buffers(torch, ctx, blocks, steps, warmup):
     """the host-buffer C-ABI calls on pinned memory, one block at a time; returns (wall ms, device ms) per step"""
-    def step():
+    copies = {"h2d_ms": 0.0, "d2h_ms": 0.0, "bytes": 0}
+
+    def step(count=False):
         t0 = time.perf_counter()
         dev_ms = 0.0
         for b in blocks.items:
@@ -407,14 +435,19 @@ def host_buffers(torch, ctx, blocks, steps, warmup):
             ctx.inverse_host_ptr(b["host_mid"].data_ptr(), b["n"], b["host_back"].data_ptr())
             si = ctx.stats()
             dev_ms += sum(s["h2d_ms"] + s["total_ms"] + s["d2h_ms"] for s in (sf, si))
+            if count:
+                copies["h2d_ms"] += sf["h2d_ms"] + si["h2d_ms"]; copies["d2h_ms"] += sf["d2h_ms"] + si["d2h_ms"]
+                copies["bytes"] += 2 * b["n"]
         return (time.perf_counter() - t0) * 1e3, dev_ms
 
     for _ in range(warmup):
         step()
-    res = [step() for _ in range(steps)]
+    res = [step(True) for _ in range(steps)]
     for b in blocks.items:
         assert torch.equal(b["host_back"], b["host_in"]), "e2e round trip lost data"
-    return sum(w for w, _ in res) / steps, sum(d for _, d in res) / steps
+    h2d_gbs = copies["bytes"] / (copies["h2d_ms"] * 1e-3) / 1e9 if copies["h2d_ms"] > 0 else 0.0
+    d2h_gbs = copies["bytes"] / (copies["d2h_ms"] * 1e-3) / 1e9 if copies["d2h_ms"] > 0 else 0.0
+    return sum(w for w, _ in res) / steps, sum(d for _, d in res) / steps, h2d_gbs, d2h_gbs
 
 
 def blocks_call(torch, bwts, items, devices, steps, warmup, golden, pinned=True):
@@ -520,6 +553,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = pin_to_gpu_numa_node(torch, local_rank)
     kind_name, seed, n, desc = WORKLOADS[args.workload]
     plan = plan_blocks(args.workload, rank, world)
     golden = golden_table()
@@ -559,7 +593,7 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     # ---- end to end: the host-buffer C-ABI call, pinned host memory, both copies inside
     barrier()
-    e2e_wall_ms, e2e_dev_ms = host_buffers(torch, ctx, blocks, args.steps, min(args.warmup, 2))
+    e2e_wall_ms, e2e_dev_ms, h2d_gbs, d2h_gbs = host_buffers(torch, ctx, blocks, args.steps, min(args.warmup, 2))
 
     # ---- several blocks per GPU: the block pipeline (bwts_b200_*_blocks: H2D of block b+1 |
     # transform of block b | D2H of block b-1), whole call timed on the host clock
@@ -573,9 +607,13 @@ def run_gpu_arm(args, rank, local_rank, world):
     # ---- max over ranks (times), sum over ranks (bytes)
     t = torch.tensor([total_ms, fwd_ms, inv_ms, e2e_wall_ms, e2e_dev_ms, pipe_ms or 0.0], dtype=torch.float64, device=dev)
     nb = torch.tensor([float(my_bytes), float(len(checked))], dtype=torch.float64, device=dev)
+    # slowest rank's copy rates (min over ranks): the host side of the PCIe copies is what limits e2e scaling
+    cp = torch.tensor([-h2d_gbs, -d2h_gbs], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(nb, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cp, op=dist.ReduceOp.MAX)
+    h2d_min, d2h_min = (-x for x in cp.tolist())
     total_ms, fwd_ms, inv_ms, e2e_wall_ms, e2e_dev_ms, pipe_ms_max = t.tolist()
     job_bytes, golden_checked = nb.tolist()
     ms_per_step = total_ms / args.steps
@@ -618,6 +656,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             "e2e": {"value": job_bytes / MB / (e2e_dev_ms * 1e-3), "unit": "MB/s",
                     "h2d_bytes_per_step": 2 * my_bytes, "d2h_bytes_per_step": 2 * my_bytes,
                     "wall_value": job_bytes / MB / (e2e_wall_ms * 1e-3),
+                    "h2d_gbs_slowest_rank": h2d_min, "d2h_gbs_slowest_rank": d2h_min, "numa_rank0": numa,
                     "how": "bwts_b200_forward_host + bwts_b200_inverse_host on pinned host buffers; CUDA events "
                            "from before the H2D copy to after the D2H copy (wall_value: host clock)"},
             "gpu_launches": launches,

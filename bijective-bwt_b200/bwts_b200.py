@@ -17,7 +17,7 @@ LIB_PATH = _HERE / "libbwts_b200.so"
 
 NCLASS = 16
 NPHASE = 8
-MAX_LEN = 1 << 30
+MAX_LEN = (1 << 31) - 1
 
 EXPORTS = [
     "bwts_b200_forward", "bwts_b200_inverse", "bwts_b200_forward_blocks", "bwts_b200_inverse_blocks",

@@ -189,9 +189,11 @@ static T *arena_take(bwts_b200_ctx *ctx, size_t count)
 }
 static size_t workspace_bytes(size_t n)
 {
-    // forward is the larger of the two: L set keys 2x8 + idx/grp/gst 2x4 each, S set keys 8 +
-    // idx/grp/gst 2x4 each, rank 4, FS 4, flags 1, onesweep status n, misc
-    return n * 114 + (64u << 20);
+    // forward is the larger of the two (bytes per input byte): L set keys 2 x 8 and idx 2 x 4 (radix
+    // ping-pong), grp / gst / gid 4 each (compacted in place), S set key2 / idx / grp / gst 4 each,
+    // rank 4, FS 4 (worst case: n factors), flags 1, onesweep status 0.5, tile tables ~0.03
+    // = 61.5; the inverse needs ~34 (prev 4, cycle tables 16, staged bytes 4, fallback records 8, ...)
+    return n * 62 + (64u << 20);
 }
 
 static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
@@ -300,9 +302,9 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     sb.cur = 0;
     sb.hist = arena_take<u32>(ctx, RADIX_MAX_PASSES * RADIX_BINS + RADIX_MAX_PASSES);
     sb.status = arena_take<u64>(ctx, (size_t)os_tiles * RADIX_BINS);
-    u32 *grp[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
-    u32 *gst[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
-    u32 *gid[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};  // dense group index of the L set
+    // one array each: the re-rank compacts in place (k_rerank, "IN PLACE")
+    u32 *grp = arena_take<u32>(ctx, n), *gst = arena_take<u32>(ctx, n);
+    u32 *gid = arena_take<u32>(ctx, n);  // dense group index of the L set (written by the re-rank, read by k_build_keys)
     u32 *rank = arena_take<u32>(ctx, n);
     u32 *FS = arena_take<u32>(ctx, (size_t)n + 1);
     u32 *cidx = arena_take<u32>(ctx, (size_t)nblk + 2);
@@ -310,15 +312,12 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     u32 *tilecnt = arena_take<u32>(ctx, ntl + 1);
     u64 *rr_statusA = arena_take<u64>(ctx, rr_tiles + 1);
     u64 *rr_statusB = arena_take<u64>(ctx, rr_tiles + 1);
-    u64 *kS = arena_take<u64>(ctx, n);
-    u32 *vS[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
-    u32 *grpS[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
-    u32 *gstS[2] = {arena_take<u32>(ctx, n), arena_take<u32>(ctx, n)};
+    u32 *kS = arena_take<u32>(ctx, n);   // S set: key2 of the last warp-local sort
+    u32 *vS = arena_take<u32>(ctx, n), *grpS = arena_take<u32>(ctx, n), *gstS = arena_take<u32>(ctx, n);
     u32 *small = arena_take<u32>(ctx, 1024);  // [0] F, [1] lmax, [2] sigma, [8..15] presence, [16..] rerank counters
     u8 *code = (u8 *)arena_take<u32>(ctx, 64);
-    if (!sb.k[0] || !sb.k[1] || !sb.v[0] || !sb.v[1] || !sb.hist || !sb.status || !grp[0] || !grp[1] || !gst[0] ||
-        !gst[1] || !gid[0] || !gid[1] || !rank || !FS || !cidx || !flags || !tilecnt || !rr_statusA || !rr_statusB || !small || !code || !kS ||
-        !vS[0] || !vS[1] || !grpS[0] || !grpS[1] || !gstS[0] || !gstS[1])
+    if (!sb.k[0] || !sb.k[1] || !sb.v[0] || !sb.v[1] || !sb.hist || !sb.status || !grp || !gst || !gid || !rank || !FS ||
+        !cidx || !flags || !tilecnt || !rr_statusA || !rr_statusB || !small || !code || !kS || !vS || !grpS || !gstS)
         return BWTS_B200_EINTERNAL;
     RerankCounters *rrc = (RerankCounters *)(small + 16);
 
@@ -410,28 +409,27 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
 
     // Two live sets.  L: groups of any size, sorted by the global radix path (sb, grp, gst).
     // S: groups of at most 32 members, sorted warp-locally (kS, vS, grpS, gstS).
-    int g = 0, gs = 0, cs = 0;       // current buffers of grp/gst (L), grpS/gstS, vS
     u32 mL = n, mS = 0, groups_before = 1, groupsL = 0;
     u64 k = k0;
     const u32 kb = linear ? bit_length(n) : max(1, bit_length((u64)n - 1));
     bool first = true, sortedL = true;  // the L set enters the loop freshly sorted (initial sort)
     bool sortedS = false;
+    const LiveOut none = {nullptr, nullptr, nullptr, nullptr};
     for (;;) {
         // ---- re-rank what was just sorted; S first, L appends to the same S stream
         ctx->phase = PH_ISA;
         CK(cudaMemsetAsync(rrc, 0, 2 * sizeof(RerankCounters), st));
-        LiveOut oS = {vS[cs], grpS[gs ^ 1], gstS[gs ^ 1], nullptr};
+        const LiveOut oS = {vS, grpS, gstS, nullptr};  // in place
         if (mS && sortedS) {
             CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
             CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
-            LiveOut none = {nullptr, nullptr, nullptr, nullptr};
-            LAUNCH(KC_RERANK, 24.0 * mS, k_rerank<false>, cdiv(mS, RR_TILE), RR_NT, kS, vS[cs ^ 1], grpS[gs],
-                   gstS[gs], mS, 0, rank, oS, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr);
+            LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<false, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
+                   (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr);
         }
         if (mL && sortedL) {
             CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
             CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
-            LiveOut oL = {sb.v[sb.cur ^ 1], grp[g ^ 1], gst[g ^ 1], gid[g ^ 1]};
+            const LiveOut oL = {sb.v[sb.cur ^ 1], grp, gst, gid};  // grp / gst in place, idx into the idle half
             // First re-rank of a large input: all n ranks are written, at random text positions
             // (the kernel then runs at the DRAM random-access rate: 2.8 ms for 64 Mi elements, ncu:
             // 85 B moved per element).  Instead the ranks go out in sorted order, one u32 onesweep
@@ -440,18 +438,19 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             const bool binned = first && use_binned_scatter(n, kb);
             u32 *nr_out = binned ? (u32 *)sb.k[sb.cur ^ 1] : (u32 *)nullptr;  // the idle key buffer: 8n bytes
             if (g_tune_local) {
-                LiveOut none = {nullptr, nullptr, nullptr, nullptr};
-                LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<false>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
-                       first ? (const u32 *)nullptr : grp[g], gst[g], mL, 0, rank, oL, (const u32 *)nullptr, none,
+                LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<false, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
+                       first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oL, (const u32 *)nullptr, none,
                        rr_statusA, rr_statusB, rrc + 1, nr_out);
             } else {
-                LAUNCH(KC_RERANK, 24.0 * mL, k_rerank<true>, cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
-                       first ? (const u32 *)nullptr : grp[g], gst[g], mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL,
+                LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<true, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
+                       first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL,
                        rr_statusA, rr_statusB, rrc + 1, nr_out);
             }
         }
         if (mL && sortedL && first && use_binned_scatter(n, kb)) {
-            u32 *nr_buf = (u32 *)sb.k[sb.cur ^ 1], *bin_pos = nr_buf + (((size_t)n + 3) & ~(size_t)3), *bin_val = grp[g];  // 16-byte aligned; grp[g] is idle in the first round
+            // scratch: rank stream + binned positions in the idle key buffer, binned ranks in kS (the S set is still empty... its
+            // key2 array is first written by the warp-local sort of the coming round)
+            u32 *nr_buf = (u32 *)sb.k[sb.cur ^ 1], *bin_pos = nr_buf + (((size_t)n + 3) & ~(size_t)3), *bin_val = kS;
             const u32 shift = kb - 8;
             LAUNCH(KC_RERANK, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
             do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
@@ -491,8 +490,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         ctx->stats.class_bytes[KC_RERANK] += 12.0 * ((double)newS + newL);
         const bool split = headsS + headsL != groups_before;
         // adopt the compacted arrays
-        if (mL && sortedL) { sb.cur ^= 1; g ^= 1; }   // idx of L now lives in sb.v[cur]
-        if (!g_tune_local) gs ^= 1;                    // S stream was written to vS[cs], grpS/gstS[gs^1]
+        if (mL && sortedL) sb.cur ^= 1;   // idx of L now lives in sb.v[cur]
         mS = newS;
         mL = newL;
         groups_before = kheadsS + kheadsL_all;
@@ -502,21 +500,20 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         if (!split || deep_enough) {
             if (linear) return BWTS_B200_EINTERNAL;  // suffixes are pairwise distinct
             // ties are final: give every member of a tie its own slot
-            LiveOut none = {nullptr, nullptr, nullptr, nullptr};
             if (mS) {
                 CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
-                LAUNCH(KC_RERANK, 16.0 * mS, k_rerank<false>, cdiv(mS, RR_TILE), RR_NT, (const u64 *)nullptr, vS[cs],
-                       grpS[gs], gstS[gs], mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc,
+                LAUNCH(KC_RERANK, 16.0 * mS, (k_rerank<false, u32>), cdiv(mS, RR_TILE), RR_NT, (const u32 *)nullptr, vS,
+                       grpS, gstS, mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc,
                        (u32 *)nullptr);
             }
             if (mL) {
                 CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rrc + 1, 0, sizeof(RerankCounters), st));
-                LAUNCH(KC_RERANK, 16.0 * mL, k_rerank<false>, cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
-                       sb.v[sb.cur], grp[g], gst[g], mL, 1, rank, none, (const u32 *)nullptr, none, rr_statusA,
+                LAUNCH(KC_RERANK, 16.0 * mL, (k_rerank<false, u64>), cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
+                       sb.v[sb.cur], grp, gst, mL, 1, rank, none, (const u32 *)nullptr, none, rr_statusA,
                        rr_statusB, rrc + 1, (u32 *)nullptr);
             }
             break;
@@ -528,9 +525,9 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         ctx->stats.live_sum += (long)mS + mL;
         sortedS = sortedL = false;
         if (mS) {
-            // every group fits a warp: gather + in-register ordering, no radix passes
-            LAUNCH(KC_LOCAL_SORT, 32.0 * mS, k_local_sort_warp, cdiv((u64)cdiv(mS, 32) * 32, 256), 256, vS[cs],
-                   gstS[gs], mS, rank, FS, cidx, (u32)k, kb, n, linear, kS, vS[cs ^ 1]);
+            // every group fits a warp: gather + in-register ordering, no radix passes; sorted in place
+            LAUNCH(KC_LOCAL_SORT, 24.0 * mS, k_local_sort_warp, cdiv((u64)cdiv(mS, 32) * 32, 256), 256, vS, gstS, mS, rank, FS,
+                   cidx, (u32)k, kb, n, linear, kS, vS);
             ctx->stats.local_rounds++;
             sortedS = true;
         }
@@ -539,7 +536,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             bool cta_sorted = false;
             if (!g_tune_nocta) {
                 CK(cudaMemsetAsync(small + 5, 0, 4, st));
-                LAUNCH(KC_LOCAL_SORT, 0, k_ls_probe, cdiv(cdiv(mL, LS_T), 256), 256, gst[g], mL, small + 5);
+                LAUNCH(KC_LOCAL_SORT, 0, k_ls_probe, cdiv(cdiv(mL, LS_T), 256), 256, gst, mL, small + 5);
                 rc = readback(ctx, st, small + 5, 4);
                 if (rc) return rc;
                 if (ctx->h_small[0] == 0) {
@@ -548,10 +545,10 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                     if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
                     if (!linear)
                         k_local_sort_cta<false><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
-                            sb.v[sb.cur], gst[g], mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                            sb.v[sb.cur], gst, mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
                     else
                         k_local_sort_cta<true><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
-                            sb.v[sb.cur], gst[g], mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                            sb.v[sb.cur], gst, mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
                     if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
                     r__.phase = ctx->phase; ctx->recs.push_back(r__);
                     CK(cudaGetLastError());
@@ -563,7 +560,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             if (!cta_sorted) {
                 // high part of the key: the dense group index (fewest bits); with routing off the
                 // group start offset does the same job
-                const u32 *hi = groupsL ? gid[g] : gst[g];
+                const u32 *hi = groupsL ? gid : gst;
                 const int hibits = max(1, bit_length(groupsL ? (u64)groupsL - 1 : (u64)mL - 1));
                 const int passes = max(1, (int)cdiv((u64)kb + hibits, 8));
                 rc = radix_prepare(ctx, st, sb);
@@ -684,11 +681,13 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     if (!spl || !jm[0] || !jm[1] || !jm[2] || !pv[0] || !pv[1] || !wlen || !minfo || !srec) return BWTS_B200_EINTERNAL;
     u32 *blkoff = nullptr, *nxt = nullptr, *cont = nullptr;
     u8 *stage = nullptr;
+    // bytes parked per sublist: 4 x the mean sublist length (e^-4 = 1.8 % of the elements lie beyond)
+    const u32 slot = min((u32)INV_SLOT_MAX, max(32u, (4u << (32 - shift)) & ~31u));
     if (staged) {
         blkoff = arena_take<u32>(ctx, (size_t)(n >> 6) + 2);
         nxt = arena_take<u32>(ctx, ns);
         cont = arena_take<u32>(ctx, ns);
-        stage = arena_take<u8>(ctx, (size_t)ns * INV_SLOT);
+        stage = arena_take<u8>(ctx, (size_t)ns * slot);
         if (!blkoff || !nxt || !cont || !stage) return BWTS_B200_EINTERNAL;
     }
     LAUNCH(KC_INV_WALK, 8.0 * ns, k_inv_spl_write, nst, 256, n, shift, tilecnt, spl, staged ? (u32 *)nullptr : sid, blkoff);
@@ -702,7 +701,7 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
         u32 Q = g_tune_invq > 0 ? (u32)g_tune_invq : max(64u, cdiv(ns, wave));
         const u32 nwarps = cdiv(ns, Q);
         LAUNCH(KC_INV_WALK, 5.0 * n, k_inv_walk_stage, cdiv(nwarps, 8), 256, prev, shift, spl, ns, Q, Ctab, nxt, wlen, minfo,
-               stage, cont, g_tune_nomark ? (u32 *)nullptr : visited, small + 2);
+               stage, slot, cont, g_tune_nomark ? (u32 *)nullptr : visited, small + 2);
         LAUNCH(KC_INV_WALK, 20.0 * ns, k_inv_resolve_next, cdiv(ns, 256), 256, nxt, minfo, blkoff, shift, ns, jm[0]);
     } else {
         LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
@@ -750,8 +749,8 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     ctx->phase = 4;
     LAUNCH(KC_INV_PLACE, 44.0 * ns, k_inv_spl_record, gs, 256, jmR, pv[pc], cyc, off, ns, srec);
     if (staged) {
-        LAUNCH(KC_INV_PLACE, 2.0 * n + 20.0 * ns, k_inv_place_copy, cdiv(ns, 8), 256, stage, wlen, srec, ns, n, d_out);
-        LAUNCH(KC_INV_PLACE, 8.0 * ns, k_inv_walk_tail, cdiv(ns, 128), 128, prev, n, shift, wlen, cont, ns, srec, Ctab, d_out);
+        LAUNCH(KC_INV_PLACE, 2.0 * n + 20.0 * ns, k_inv_place_copy, cdiv(ns, 8), 256, stage, wlen, srec, ns, n, slot, d_out);
+        LAUNCH(KC_INV_PLACE, 8.0 * ns, k_inv_walk_tail, cdiv(ns, 128), 128, prev, n, shift, wlen, cont, ns, slot, srec, Ctab, d_out);
     } else {
         LAUNCH(KC_INV_PLACE, 5.0 * n, k_inv_walk_place, cdiv(ns, 128), 128, prev, n, shift, spl, ns, srec, Ctab, d_out);
     }
@@ -1282,7 +1281,7 @@ extern "C" const char *bwts_b200_strerror(int code)
     switch (code) {
     case BWTS_B200_OK: return "ok";
     case BWTS_B200_EINVAL: return "invalid argument";
-    case BWTS_B200_ETOOBIG: return "input longer than 2^30 bytes per block";
+    case BWTS_B200_ETOOBIG: return "input of 2^31 bytes or more per block";
     case BWTS_B200_ENODEV: return "no usable CUDA device (there is no CPU fallback)";
     case BWTS_B200_ENOMEM: return "out of device or pinned host memory";
     case BWTS_B200_ECUDA: return "CUDA error";

@@ -209,27 +209,39 @@ struct LiveOut {  // one compaction stream
 // grp == nullptr (with gst ignored): both arrays are all zero -- the first re-rank after the
 // initial sort, where the whole text is one group of rank 0 starting at slot 0.
 // ROUTE: decide S/L per group (otherwise everything kept goes to S, used for the S set itself).
+// KeyT: u64 radix keys (L set) or the bare u32 key2 = rank[succ^k] (S set: inside a group the high
+// part of the radix key is the same for all members, so equal key2 <=> equal key).
 // finalize != 0: every element becomes its own group (ties are known to be final); no outputs.
 // baseS: device word holding the number of elements already in the S stream (nullptr = 0).
 // nr_out != nullptr: the new rank of slot j is stored at nr_out[j] instead of being scattered to
 // rank[idx[j]]; the caller bins the (idx, rank) pairs by text region and scatters them with
 // locality (first re-rank of large inputs, where every one of the n ranks is written).
-template <bool ROUTE>
-__global__ void __launch_bounds__(RR_NT, 4) k_rerank(const u64 *__restrict__ keys, const u32 *__restrict__ idx,
-                                                  const u32 *__restrict__ grp, const u32 *__restrict__ gst, u32 m,
+//
+// IN PLACE: outS / outL may alias the input arrays (idx, grp, gst).  A tile writes its kept
+// elements at [exclusive prefix, +kept), which never lies beyond its own input region, and it
+// learns that prefix only after every earlier tile has published its counts.  A tile publishes
+// after a barrier that follows a shared-memory store of a value computed from EVERY input word
+// it loaded (s_sink): its input is in registers -- not merely requested -- before any later
+// tile can start writing.  Inputs are read with ld.global.cg (L2, coherent), not through the
+// non-coherent path.  This halves the doubling state: one grp / gst / idx array per set.
+template <bool ROUTE, typename KeyT>
+__global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ keys, const u32 *idx,
+                                                  const u32 *grp, const u32 *gst, u32 m,
                                                   int finalize, u32 *__restrict__ rank, LiveOut outS,
                                                   const u32 *__restrict__ baseS, LiveOut outL,
                                                   u64 *__restrict__ statusA, u64 *__restrict__ statusB,
                                                   RerankCounters *__restrict__ ctr, u32 *__restrict__ nr_out)
 {
-    __shared__ u8 s_hb[RR_NT + 8];  // head flags of the tile, 8 slots per byte, + the slot after the tile
+    __shared__ __align__(16) u32 s_hw[RR_NT / 4 + 4];  // head flags of the tile as a bit array (slot = bit), + the slots after it
+    __shared__ u32 s_sink[RR_NT];
     __shared__ u32 s_wh[RR_NT / 32], s_ws[RR_NT / 32], s_wl[RR_NT / 32], s_wg[RR_NT / 32];
     __shared__ u32 s_nh[RR_NT / 32], s_nk[RR_NT / 32];
     __shared__ u32 s_exh, s_exs, s_exl, s_exg;
+    u8 *s_hb = (u8 *)s_hw;  // byte t = the 8 slots of thread t
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     PH_INIT();
-    if (tid < 8) s_hb[RR_NT + tid] = 0;
+    if (tid < 4) s_hw[RR_NT / 4 + tid] = 0;
     __syncthreads();
     // tile = blockIdx.x: CTAs are dispatched in index order, so the tiles a look-back waits for
     // are resident or finished (same assumption as the onesweep kernel)
@@ -238,35 +250,43 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const u64 *__restrict__ key
 
     // ---- my 8 slots, loaded up front (vector loads when the whole stretch is in range)
     u32 vi[RR_IPT], vg[RR_IPT], vs[RR_IPT];
-    u64 vk[RR_IPT];
+    KeyT vk[RR_IPT];
     const bool full = (u64)j0 + RR_IPT <= m;
     if (full) {
 #pragma unroll
         for (int q = 0; q < RR_IPT / 4; q++) {
-            const uint4 a = ldg_stream_u4((const uint4 *)(idx + j0) + q);
+            const uint4 a = __ldcg((const uint4 *)(idx + j0) + q);
             const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-            const uint4 b = grp ? ldg_stream_u4((const uint4 *)(grp + j0) + q) : z4;
-            const uint4 c = grp ? ldg_stream_u4((const uint4 *)(gst + j0) + q) : z4;
+            const uint4 b = grp ? __ldcg((const uint4 *)(grp + j0) + q) : z4;
+            const uint4 c = grp ? __ldcg((const uint4 *)(gst + j0) + q) : z4;
             vi[4 * q] = a.x; vi[4 * q + 1] = a.y; vi[4 * q + 2] = a.z; vi[4 * q + 3] = a.w;
             vg[4 * q] = b.x; vg[4 * q + 1] = b.y; vg[4 * q + 2] = b.z; vg[4 * q + 3] = b.w;
             vs[4 * q] = c.x; vs[4 * q + 1] = c.y; vs[4 * q + 2] = c.z; vs[4 * q + 3] = c.w;
         }
         if (!finalize) {
+            if (sizeof(KeyT) == 8) {
 #pragma unroll
-            for (int q = 0; q < RR_IPT / 2; q++) {
-                const uint4 a = __ldg((const uint4 *)(keys + j0) + q);
-                vk[2 * q] = ((u64)a.y << 32) | a.x;
-                vk[2 * q + 1] = ((u64)a.w << 32) | a.z;
+                for (int q = 0; q < RR_IPT / 2; q++) {
+                    const uint4 a = __ldcg((const uint4 *)(keys + j0) + q);
+                    vk[2 * q] = (KeyT)(((u64)a.y << 32) | a.x);
+                    vk[2 * q + 1] = (KeyT)(((u64)a.w << 32) | a.z);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < RR_IPT / 4; q++) {
+                    const uint4 a = __ldcg((const uint4 *)(keys + j0) + q);
+                    vk[4 * q] = (KeyT)a.x; vk[4 * q + 1] = (KeyT)a.y; vk[4 * q + 2] = (KeyT)a.z; vk[4 * q + 3] = (KeyT)a.w;
+                }
             }
         }
     } else {
 #pragma unroll
         for (int q = 0; q < RR_IPT; q++) {
             const bool in = (u64)j0 + q < m;
-            vi[q] = in ? idx[j0 + q] : 0;
-            vg[q] = (in && grp) ? grp[j0 + q] : 0;
-            vs[q] = (in && grp) ? gst[j0 + q] : 0;
-            vk[q] = (in && !finalize) ? keys[j0 + q] : 0;
+            vi[q] = in ? __ldcg(idx + j0 + q) : 0;
+            vg[q] = (in && grp) ? __ldcg(grp + j0 + q) : 0;
+            vs[q] = (in && grp) ? __ldcg(gst + j0 + q) : 0;
+            vk[q] = (in && !finalize) ? __ldcg(keys + j0 + q) : (KeyT)0;
         }
     }
     const u32 mine = (j0 >= m) ? 0u : min((u32)RR_IPT, m - j0);  // slots of mine that exist
@@ -275,8 +295,8 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const u64 *__restrict__ key
     if (finalize) {
         hbits = 0x1ffu;
     } else {
-        u64 prevk = 0;
-        if (j0 > 0 && j0 < m) prevk = __ldg(keys + j0 - 1);
+        KeyT prevk = 0;
+        if (j0 > 0 && j0 < m) prevk = __ldcg(keys + j0 - 1);
 #pragma unroll
         for (int q = 0; q < RR_IPT; q++) {
             if ((u32)q < mine) {
@@ -286,10 +306,17 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const u64 *__restrict__ key
         }
         const u64 jn = (u64)j0 + RR_IPT;
         bool hn = true;
-        if (jn < m) hn = ((grp ? __ldg(gst + jn) : 0u) == (u32)jn) || (__ldg(keys + jn) != vk[RR_IPT - 1]);
+        if (jn < m) hn = ((grp ? __ldcg(gst + jn) : 0u) == (u32)jn) || (__ldcg(keys + jn) != vk[RR_IPT - 1]);
         hbits |= (u32)hn << RR_IPT;
     }
     if (mine < RR_IPT) hbits |= 1u << mine;  // the slot after the last live slot acts as a head
+    {
+        // every input word is in a register before the barrier below (see IN PLACE above)
+        u32 x = hbits;
+#pragma unroll
+        for (int q = 0; q < RR_IPT; q++) x ^= vi[q] ^ vg[q] ^ vs[q];
+        s_sink[tid] = x;
+    }
     s_hb[tid] = (u8)hbits;
     if (tid == RR_NT - 1) s_hb[RR_NT] = (u8)(hbits >> RR_IPT);
     PH(16);  // loads + head flags
@@ -297,18 +324,21 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const u64 *__restrict__ key
     PH(17);
 
     // ---- per slot: keep?  which stream?
-    // next head strictly after tile slot hs, looked for in the following 32 slots
-    auto group_small = [&](u32 hs) -> bool {
-        const u32 b0 = hs + 1;
-        const u32 by = b0 >> 3;
-        u64 wbits = 0;
-#pragma unroll
-        for (int t = 0; t < 6; t++) {
-            const u32 bi = by + t;
-            wbits |= (u64)(bi <= RR_NT ? s_hb[bi] : 0) << (8 * t);
-        }
-        const u32 w32 = (u32)(wbits >> (b0 & 7));
-        return w32 != 0;  // a head within 32 slots: the group has at most 32 members
+    // A group goes to S when its head and the next head both lie in this tile's bit array and are at
+    // most 32 slots apart.  Bit scans over the head bits (64-bit windows assembled from the words).
+    auto head_at_or_before = [&](u32 x) -> int {  // tile slot of the last head in (x - 32, x], or -1
+        const u32 w = x >> 5;
+        const u64 two = ((u64)s_hw[w] << 32) | (u64)(w ? s_hw[w - 1] : 0u);
+        const u32 pos = 32 + (x & 31);  // bit of slot x inside `two`
+        const u64 upto = two & ((pos == 63) ? ~0ull : (((u64)2 << pos) - 1));
+        if (!upto) return -1;
+        const u32 hb = 63u - (u32)__clzll((long long)upto);
+        if (pos - hb >= 32) return -1;
+        return (int)(x - (pos - hb));
+    };
+    auto group_small = [&](u32 hs) -> bool {  // a head among the 32 slots after tile slot hs
+        const u32 b0 = hs + 1, w = b0 >> 5;
+        return __funnelshift_r(s_hw[w], s_hw[w + 1], b0 & 31) != 0;
     };
     u32 kbits = 0, sbits = 0;  // keep, keep-in-S
     u32 lasth = 0, nS = 0, nL = 0, nG = 0, nhead = 0, nkhead = 0;  // nG: kept heads that go to L
@@ -330,17 +360,8 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const u64 *__restrict__ key
                     if (!ROUTE) {
                         route = 1;
                     } else if (route < 0) {
-                        // find my group's head inside the tile
-                        int hs = (int)(tid * RR_IPT) + q;
-                        if (!h) {
-                            // walk back over the head bytes (at most 32 slots matter)
-                            int found = -1;
-                            for (int back = 1; back <= RR_SMALL && hs - back >= 0; back++) {
-                                const int sl = hs - back;
-                                if ((s_hb[sl >> 3] >> (sl & 7)) & 1) { found = sl; break; }
-                            }
-                            hs = found;
-                        }
+                        const u32 x = tid * RR_IPT + q;
+                        const int hs = h ? (int)x : head_at_or_before(x);
                         route = (hs >= 0 && group_small((u32)hs)) ? 1 : 0;
                     }
                     kbits |= 1u << q;
@@ -508,11 +529,14 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const u64 *__restrict__ key
 // Warp w owns the whole groups between the group holding live slot 32w and the group holding
 // slot 32w+32 (at most 63 slots): gather key2 = rank[succ^k(idx)], order the slots by
 // (group, key2) by counting, write keys / idx in the layout the radix path would have produced.
-__global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *__restrict__ idx, const u32 *__restrict__ gst,
+// keys_out receives the bare key2 (u32): the group part of the key is position-indexed state (gst).
+// idx_out may alias idx: a warp reads all of its slots before it writes any, and no other warp
+// touches them.
+__global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *idx, const u32 *__restrict__ gst,
                                                          u32 m, const u32 *__restrict__ rank,
                                                          const u32 *__restrict__ FS, const u32 *__restrict__ cidx,
                                                          u32 k, u32 kb, u32 n, int linear,
-                                                         u64 *__restrict__ keys_out, u32 *__restrict__ idx_out)
+                                                         u32 *__restrict__ keys_out, u32 *idx_out)
 {
     const u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u32 lane = lane_id();
@@ -529,7 +553,7 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *__restrict__
         pay[h] = 0;
         if (t < cnt) {
             const u32 j = lo + t;
-            const u32 i = ldg_stream_u32(idx + j);
+            const u32 i = __ldcg(idx + j);
             const u32 g = ldg_stream_u32(gst + j);
             u32 r;
             if (linear) {
@@ -585,7 +609,7 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *__restrict__
 #pragma unroll
     for (int h = 0; h < 2; h++)
         if (lane + 32 * h < cnt) {
-            keys_out[lo + gs[h] + pos[h]] = key[h];
+            keys_out[lo + gs[h] + pos[h]] = r[h];
             idx_out[lo + gs[h] + pos[h]] = pay[h];
         }
 }
@@ -655,8 +679,15 @@ __global__ void __launch_bounds__(LS_NT, 2) k_local_sort_cta(const u32 *__restri
     }
     __syncthreads();
 
+    // Already in order?  On repetitive inputs (the tiled C3 text) most groups see one and the same
+    // key2 for all of their members in most rounds -- the network would move nothing.  One pass
+    // over the staged words decides; keys are distinct (the slot is part of them).
+    bool unsorted = false;
+    for (u32 s = tid; s + 1 < cnt; s += LS_NT) unsorted |= s_key[s] > s_key[s + 1];
+    const bool need_sort = __syncthreads_or(unsorted);
+
     // bitonic network; strides below 8 run in registers on 8 consecutive words per thread
-    for (u32 k2 = 2; k2 <= P; k2 <<= 1) {
+    for (u32 k2 = 2; need_sort && k2 <= P; k2 <<= 1) {
         u32 j = k2 >> 1;
         for (; j >= 8; j >>= 1) {
             for (u32 t = tid; t < P / 2; t += LS_NT) {

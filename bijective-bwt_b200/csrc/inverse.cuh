@@ -401,14 +401,14 @@ __global__ void __launch_bounds__(256) k_inv_spl_record(const u64 *__restrict__ 
 // 4-byte step, 22x the algorithmic bytes, lanes idle 3/4 of the time because a warp runs until its
 // longest sublist ends).  Here the first walk already recovers the bytes: the byte of element i is
 // the c with C[c] <= prev[i] < C[c+1], and the walker of sublist s parks it at stage[s][offset]
-// (INV_SLOT bytes per sublist, written as full 32-byte sectors).  After the list ranking a
+// (slot bytes per sublist, written as full 32-byte sectors).  After the list ranking a
 // streaming kernel copies every slot to its place in the output (a sublist is at most two
-// descending runs there); only the 1.8 % of the elements beyond offset INV_SLOT of their sublist
+// descending runs there); only the 1.8 % of the elements beyond offset slot of their sublist
 // are chased a second time, from the element the first walk parked in cont[s].
 // Lanes are refilled: warp w owns the sublists [w Q, (w+1) Q) and a lane whose sublist ended takes
 // the next one of the warp's range (ballot + popc, no atomics), so the warp stays full until its
 // range runs dry.
-#define INV_SLOT 256
+#define INV_SLOT_MAX 256  // staged bytes per sublist (`slot`): 4 x the mean sublist length, a multiple of 32, at most this
 
 static __device__ __forceinline__ u32 byte_of_rank(const u32 *sC, u32 p)
 {
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ 
                                                         const u32 *__restrict__ spl, u32 ns, u32 Q,
                                                         const u32 *__restrict__ Ctab, u32 *__restrict__ nxt,
                                                         u32 *__restrict__ wlen, uint2 *__restrict__ minfo,
-                                                        u8 *__restrict__ stage, u32 *__restrict__ cont,
+                                                        u8 *__restrict__ stage, u32 slot, u32 *__restrict__ cont,
                                                         u32 *__restrict__ visited, u32 *__restrict__ total)
 {
     __shared__ u32 sC[257];
@@ -448,13 +448,13 @@ __global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ 
                     a0 = a1 = a2 = a3 = 0;
                 }
             }
-            next += __popc(idle);
+            next = min(hi, next + (u32)__popc(idle));  // saturates: a long walk next to idle lanes must not wrap the cursor
             if (__all_sync(FULL_MASK, s == NONE32)) break;
         }
         if (s != NONE32) {
             const u32 p = ldg_stream_u32(prev + i);
             if (visited) atomicOr(visited + (i >> 5), 1u << (i & 31));
-            if (o < INV_SLOT) {
+            if (o < slot) {
                 const u32 c = byte_of_rank(sC, p);
                 const u32 b = o & 31, q = b >> 3;
                 const u64 v = (u64)c << (8 * (b & 7));
@@ -463,18 +463,18 @@ __global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ 
                 a2 |= (q == 2) ? v : 0ull;
                 a3 |= (q == 3) ? v : 0ull;
                 if (b == 31) {
-                    uint4 *dst = (uint4 *)(stage + (u64)s * INV_SLOT + (o & ~31u));
+                    uint4 *dst = (uint4 *)(stage + (u64)s * slot + (o & ~31u));
                     dst[0] = make_uint4((u32)a0, (u32)(a0 >> 32), (u32)a1, (u32)(a1 >> 32));
                     dst[1] = make_uint4((u32)a2, (u32)(a2 >> 32), (u32)a3, (u32)(a3 >> 32));
                     a0 = a1 = a2 = a3 = 0;
                 }
-            } else if (o == INV_SLOT) {
-                cont[s] = i;  // the element at offset INV_SLOT: where k_inv_walk_tail resumes
+            } else if (o == slot) {
+                cont[s] = i;  // the element at offset slot: where k_inv_walk_tail resumes
             }
             o++;
             if (is_splitter(p, shift)) {
-                if (o <= INV_SLOT && (o & 31)) {
-                    uint4 *dst = (uint4 *)(stage + (u64)s * INV_SLOT + ((o - 1) & ~31u));
+                if (o <= slot && (o & 31)) {
+                    uint4 *dst = (uint4 *)(stage + (u64)s * slot + ((o - 1) & ~31u));
                     dst[0] = make_uint4((u32)a0, (u32)(a0 >> 32), (u32)a1, (u32)(a1 >> 32));
                     dst[1] = make_uint4((u32)a2, (u32)(a2 >> 32), (u32)a3, (u32)(a3 >> 32));
                 }
@@ -505,15 +505,15 @@ __global__ void __launch_bounds__(256) k_inv_resolve_next(const u32 *__restrict_
 
 // one warp per sublist: its staged bytes go to out[top - d], d = (A + offset) mod L
 __global__ void __launch_bounds__(256) k_inv_place_copy(const u8 *__restrict__ stage, const u32 *__restrict__ wlen,
-                                                        const uint4 *__restrict__ srec, u32 ns, u32 n,
+                                                        const uint4 *__restrict__ srec, u32 ns, u32 n, u32 slot,
                                                         u8 *__restrict__ out)
 {
     const u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (s >= ns) return;
-    const u32 len = min(__ldg(wlen + s), (u32)INV_SLOT);
+    const u32 len = min(__ldg(wlen + s), slot);
     const uint4 r = __ldg(srec + s);
     const u32 L = r.y, top = n - 1 - r.z;
-    const u8 *src = stage + s * INV_SLOT;
+    const u8 *src = stage + s * slot;
     for (u32 o = lane_id(); o < len; o += 32) {
         u32 d = r.x + o;  // A < L and o < len <= L
         if (d >= L) d -= L;
@@ -521,20 +521,20 @@ __global__ void __launch_bounds__(256) k_inv_place_copy(const u8 *__restrict__ s
     }
 }
 
-// the elements beyond offset INV_SLOT of their sublist: a second walk from cont[s]
+// the elements beyond offset slot of their sublist: a second walk from cont[s]
 __global__ void __launch_bounds__(128) k_inv_walk_tail(const u32 *__restrict__ prev, u32 n, u32 shift,
                                                        const u32 *__restrict__ wlen, const u32 *__restrict__ cont,
-                                                       u32 ns, const uint4 *__restrict__ srec,
+                                                       u32 ns, u32 slot, const uint4 *__restrict__ srec,
                                                        const u32 *__restrict__ Ctab, u8 *__restrict__ out)
 {
     __shared__ u32 sC[257];
     for (u32 t = threadIdx.x; t < 257; t += blockDim.x) sC[t] = Ctab[t];
     __syncthreads();
     const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= ns || wlen[s] <= INV_SLOT) return;
+    if (s >= ns || wlen[s] <= slot) return;
     const uint4 r = srec[s];
     const u32 L = r.y, top = n - 1 - r.z;
-    u32 d = r.x + INV_SLOT;  // < 2 L
+    u32 d = r.x + slot;  // < 2 L
     if (d >= L) d -= L;
     u32 i = cont[s];
     do {

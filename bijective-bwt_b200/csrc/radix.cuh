@@ -15,7 +15,7 @@
 #define RADIX_BINS 256
 #define RADIX_MAX_PASSES 8
 
-#define OS_TILE_MIN 2048          // the status array is sized for the smallest tile a configuration may use
+#define OS_TILE_MIN 4096          // the status array is sized for the smallest tile a configuration may use
 
 #define OS_FLAG_AGG 1ull
 #define OS_FLAG_PREFIX 2ull

@@ -23,8 +23,9 @@
  * the reference's "message to stderr, exit(1)" convention.  There is no CPU
  * fallback: without a CUDA device every transform fails with BWTS_B200_ENODEV.
  *
- * Limits: 1 <= len <= 2^30 per block (32-bit ranks with two tag bits; the reference
- * is limited to len < 2^31 by `int`/`saidx_t`, mk_bwts_sa.c:26-27).
+ * Limits: 1 <= len < 2^31 per block, the reference's own range (`int` / `saidx_t`,
+ * mk_bwts_sa.c:26-27, unbwts.c:12-13).  The device workspace is 62 bytes per input byte (+ 64 MiB,
+ * + 2 per byte for the host-buffer calls): 2 GiB blocks need ~137 GB of the B200's 180 GB.
  */
 #ifndef BWTS_B200_H
 #define BWTS_B200_H
@@ -41,7 +42,7 @@ extern "C" {
 #define BWTS_B200_ECUDA     -5   /* a CUDA call or kernel failed; see bwts_b200_last_cuda_error */
 #define BWTS_B200_EINTERNAL -6   /* invariant violated (a bug)                            */
 
-#define BWTS_B200_MAX_LEN (1L << 30)
+#define BWTS_B200_MAX_LEN ((1L << 31) - 1)
 
 typedef struct bwts_b200_ctx bwts_b200_ctx;
 
@@ -79,7 +80,8 @@ int  bwts_b200_reserve(bwts_b200_ctx *ctx, long max_len);   /* pre-size the work
 int bwts_b200_forward_host(bwts_b200_ctx *ctx, const unsigned char *in, long len, unsigned char *out);
 int bwts_b200_inverse_host(bwts_b200_ctx *ctx, const unsigned char *in, long len, unsigned char *out);
 
-/* device-resident buffers (d_in, d_out: device pointers on ctx's device, not aliased).
+/* device-resident buffers (d_in, d_out: device pointers on ctx's device, not aliased; any
+ * alignment -- an input that is not 16-byte aligned costs one device-to-device copy).
  * Work is issued on `stream` (a cudaStream_t passed as void*; NULL = the context's own
  * stream).  The call returns after the result is complete in d_out (the driver loop
  * reads a few counters back per doubling round).                                      */

@@ -47,7 +47,7 @@ def test_argument_validation_needs_no_device(bwts):
     buf = np.zeros(16, dtype=np.uint8)
     assert L.bwts_b200_forward(None, 16, buf.ctypes.data, 0) == -1
     assert L.bwts_b200_inverse(buf.ctypes.data, -5, buf.ctypes.data, 0) == -1
-    assert L.bwts_b200_forward(buf.ctypes.data, (1 << 30) + 1, buf.ctypes.data, 0) == -2
+    assert L.bwts_b200_forward(buf.ctypes.data, 1 << 31, buf.ctypes.data, 0) == -2
     assert L.bwts_b200_tune(99, 1) == -1
     assert L.bwts_b200_tune(1, 5) == -1
 

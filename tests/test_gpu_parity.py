@@ -348,7 +348,7 @@ def test_one_call_entry_points_and_errors(bwts, oracle):
     assert L.bwts_b200_forward(None, 8, buf.ctypes.data, 0) == -1
     assert L.bwts_b200_forward(buf.ctypes.data, 0, buf.ctypes.data, 0) == -1
     assert L.bwts_b200_forward(buf.ctypes.data, 8, buf.ctypes.data, 999) == -1
-    assert L.bwts_b200_inverse(buf.ctypes.data, (1 << 30) + 1, buf.ctypes.data, 0) == -2
+    assert L.bwts_b200_inverse(buf.ctypes.data, 1 << 31, buf.ctypes.data, 0) == -2
 
 
 def test_device_resident_api_with_torch(bwts, ctx, oracle, gen):
