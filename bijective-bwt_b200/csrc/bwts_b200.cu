@@ -29,11 +29,11 @@
 
 enum KClass {
     KC_LYNDON = 0, KC_FACTORS, KC_INIT_KEYS, KC_RADIX_HIST, KC_ONESWEEP, KC_BUILD_KEYS, KC_RERANK, KC_EMIT,
-    KC_INV_HIST, KC_INV_LF, KC_INV_WALK, KC_INV_JUMP, KC_INV_SCAN, KC_INV_PLACE, KC_LOCAL_SORT, KC_COPY
+    KC_INV_HIST, KC_INV_LF, KC_INV_WALK, KC_INV_JUMP, KC_INV_SCAN, KC_INV_PLACE, KC_LOCAL_SORT, KC_TUPLE
 };
 static const char *kclass_names[BWTS_B200_NCLASS] = {
     "lyndon", "factor_table", "init_keys", "radix_hist", "onesweep_pass", "build_keys", "rerank", "emit",
-    "inv_tile_hist", "inv_lf_rank", "inv_walk", "inv_jump", "inv_scan", "inv_place", "local_sort", "copy"};
+    "inv_tile_hist", "inv_lf_rank", "inv_walk", "inv_jump", "inv_scan", "inv_place", "local_sort", "tuple_round"};
 
 static std::atomic<u32> g_epoch{0};  // onesweep status epoch, unique per pass across all contexts
 static long g_tune_chunk = 0;      // Lyndon chunk bytes (0 = auto)
@@ -46,6 +46,7 @@ static long g_tune_emit = 0;       // emit: 0 = binned from 512 Mi bytes, 1 = al
 static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L set
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
+static long g_tune_tmax = 0;       // tuple set: largest group it takes (0 = 8, 1 = set switched off, 2..32)
 static long g_tune_invpath = 0;    // inverse: 0 = staged single walk (default), 1 = two read-only walks (round 1)
 static long g_tune_invq = 0;       // inverse staged walk: sublists per warp (0 = auto: one full wave of warps)
 static long g_tune_nomark = 0;     // TIMING EXPERIMENT ONLY: inverse first walk without visited marks (wrong output when a cycle has no splitter)
@@ -191,9 +192,10 @@ static size_t workspace_bytes(size_t n)
 {
     // forward is the larger of the two (bytes per input byte): L set keys 2 x 8 and idx 2 x 4 (radix
     // ping-pong), grp / gst / gid 4 each (compacted in place), S set key2 / idx / grp / gst 4 each,
-    // rank 4, FS 4 (worst case: n factors), flags 1, onesweep status 0.5, tile tables ~0.03
-    // = 61.5; the inverse needs ~34 (prev 4, cycle tables 16, staged bytes 4, fallback records 8, ...)
-    return n * 62 + (64u << 20);
+    // tuple set ring links 2 x 4 and rank increments 1, rank 4, FS 4 (worst case: n factors), flags 1,
+    // onesweep status 0.5, tile tables ~0.03 = 70.5; the inverse needs ~34 (prev 4, cycle tables 16,
+    // staged bytes 4, fallback records 8, ...)
+    return n * 71 + (64u << 20);
 }
 
 static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
@@ -314,12 +316,23 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     u64 *rr_statusB = arena_take<u64>(ctx, rr_tiles + 1);
     u32 *kS = arena_take<u32>(ctx, n);   // S set: key2 of the last warp-local sort
     u32 *vS = arena_take<u32>(ctx, n), *grpS = arena_take<u32>(ctx, n), *gstS = arena_take<u32>(ctx, n);
+    // tuple set T (k_tuple_round): ring links by text position, double-buffered, + the rank increments
+    const u32 tmax = g_tune_local ? 1u : (g_tune_tmax == 0 ? 8u : (u32)g_tune_tmax);  // 1 = switched off
+    u32 *nxtT[2] = {nullptr, nullptr};
+    u8 *drT = nullptr;
+    if (tmax >= 2) {
+        nxtT[0] = arena_take<u32>(ctx, n);
+        nxtT[1] = arena_take<u32>(ctx, n);
+        drT = arena_take<u8>(ctx, n);
+        if (!nxtT[0] || !nxtT[1] || !drT) return BWTS_B200_EINTERNAL;
+    }
     u32 *small = arena_take<u32>(ctx, 1024);  // [0] F, [1] lmax, [2] sigma, [8..15] presence, [16..] rerank counters
     u8 *code = (u8 *)arena_take<u32>(ctx, 64);
     if (!sb.k[0] || !sb.k[1] || !sb.v[0] || !sb.v[1] || !sb.hist || !sb.status || !grp || !gst || !gid || !rank || !FS ||
         !cidx || !flags || !tilecnt || !rr_statusA || !rr_statusB || !small || !code || !kS || !vS || !grpS || !gstS)
         return BWTS_B200_EINTERNAL;
     RerankCounters *rrc = (RerankCounters *)(small + 16);
+    u32 *tcnt = (u32 *)(rrc + 2);  // tuple round: [0] still in the set, [1] saw a split, [2] processed; read back with rrc
 
     CK(cudaMemsetAsync(small, 0, 1024 * sizeof(u32), st));
     // The arena is re-laid-out per call, so the look-back status region may hold stale keys
@@ -405,11 +418,18 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     if (rc) return rc;
 
     CK(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
+    if (tmax >= 2) {  // every position starts outside the tuple set, in both buffers
+        CK(cudaMemsetAsync(nxtT[0], 0xff, (size_t)n * 4, st));
+        CK(cudaMemsetAsync(nxtT[1], 0xff, (size_t)n * 4, st));
+    }
     const int PH_SORT0 = 0, PH_ISA = 1, PH_FIX = 2, PH_EMIT = 3;  // bwts_b200_phase_name(0, .)
 
     // Two live sets.  L: groups of any size, sorted by the global radix path (sb, grp, gst).
     // S: groups of at most 32 members, sorted warp-locally (kS, vS, grpS, gstS).
-    u32 mL = n, mS = 0, groups_before = 1, groupsL = 0;
+    // T: groups of at most tmax members, refined in text order (nxtT, drT); they never come back.
+    u32 mL = n, mS = 0, mT = 0, groups_before = 1, groupsL = 0;
+    int tc = 0;  // nxtT[tc] holds the rings
+    const u32 tgrid = min(cdiv(n, 256), (u32)ctx->sm_count * 16u);
     u64 k = k0;
     const u32 kb = linear ? bit_length(n) : max(1, bit_length((u64)n - 1));
     bool first = true, sortedL = true;  // the L set enters the loop freshly sorted (initial sort)
@@ -423,8 +443,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         if (mS && sortedS) {
             CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
             CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
-            LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<false, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
-                   (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr);
+            if (tmax >= 2) {
+                LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<2, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
+                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, nxtT[tc], tmax);
+            } else {
+                LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<0, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
+                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, (u32 *)nullptr, 0u);
+            }
         }
         if (mL && sortedL) {
             CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
@@ -438,13 +463,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             const bool binned = first && use_binned_scatter(n, kb);
             u32 *nr_out = binned ? (u32 *)sb.k[sb.cur ^ 1] : (u32 *)nullptr;  // the idle key buffer: 8n bytes
             if (g_tune_local) {
-                LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<false, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
+                LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<0, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oL, (const u32 *)nullptr, none,
-                       rr_statusA, rr_statusB, rrc + 1, nr_out);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out, (u32 *)nullptr, 0u);
             } else {
-                LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<true, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
+                LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<1, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL,
-                       rr_statusA, rr_statusB, rrc + 1, nr_out);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out, tmax >= 2 ? nxtT[tc] : (u32 *)nullptr, tmax >= 2 ? tmax : 0u);
             }
         }
         if (mL && sortedL && first && use_binned_scatter(n, kb)) {
@@ -464,15 +489,20 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             CK(cudaGetLastError());
             LAUNCH(KC_RERANK, 12.0 * n, k_scatter_pairs, cdiv(cdiv(n, 8), 256), 256, bin_pos, bin_val, n, rank);
         }
-        rc = readback(ctx, st, rrc, 2 * sizeof(RerankCounters));
+        rc = readback(ctx, st, rrc, 2 * sizeof(RerankCounters) + 16);
         if (rc) return rc;
         const RerankCounters cS = ((const RerankCounters *)ctx->h_small)[0];
         const RerankCounters cL = ((const RerankCounters *)ctx->h_small)[1];
-        u32 headsS = 0, headsL = 0, kheadsS = 0, kheadsL_all = 0;
+        // what the tuple round of the previous iteration left (zero when none ran) + this iteration's arrivals
+        const u32 *tc_h = (const u32 *)((const RerankCounters *)ctx->h_small + 2);
+        const bool splitT = tc_h[1] != 0;
+        u32 headsS = 0, headsL = 0, kheadsS = 0, kheadsL_all = 0, enteredT = 0;
         for (int q = 0; q < RR_SPREAD; q++) {
             headsS += cS.heads[q]; headsL += cL.heads[q];
             kheadsS += cS.kheads[q]; kheadsL_all += cL.kheads[q];
+            enteredT += cS.keptT[q] + cL.keptT[q];
         }
+        mT = tc_h[0] + enteredT;
         if (first && !linear) {
             rc = readback(ctx, st, small + 1, 4);
             if (rc) return rc;
@@ -488,14 +518,14 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             newL = cL.keptL;
         }
         ctx->stats.class_bytes[KC_RERANK] += 12.0 * ((double)newS + newL);
-        const bool split = headsS + headsL != groups_before;
+        const bool split = headsS + headsL != groups_before || splitT;
         // adopt the compacted arrays
         if (mL && sortedL) sb.cur ^= 1;   // idx of L now lives in sb.v[cur]
         mS = newS;
         mL = newL;
         groups_before = kheadsS + kheadsL_all;
         groupsL = g_tune_local ? 0 : cL.kheadsL;
-        if (mS + mL == 0) break;
+        if (mS + mL + mT == 0) break;
         const bool deep_enough = !linear && k >= 2ull * lmax;  // Fine-Wilf: remaining ties are equal rotations
         if (!split || deep_enough) {
             if (linear) return BWTS_B200_EINTERNAL;  // suffixes are pairwise distinct
@@ -504,26 +534,48 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                 CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
-                LAUNCH(KC_RERANK, 16.0 * mS, (k_rerank<false, u32>), cdiv(mS, RR_TILE), RR_NT, (const u32 *)nullptr, vS,
+                LAUNCH(KC_RERANK, 16.0 * mS, (k_rerank<0, u32>), cdiv(mS, RR_TILE), RR_NT, (const u32 *)nullptr, vS,
                        grpS, gstS, mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc,
-                       (u32 *)nullptr);
+                       (u32 *)nullptr, (u32 *)nullptr, 0u);
             }
             if (mL) {
                 CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
                 CK(cudaMemsetAsync(rrc + 1, 0, sizeof(RerankCounters), st));
-                LAUNCH(KC_RERANK, 16.0 * mL, (k_rerank<false, u64>), cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
+                LAUNCH(KC_RERANK, 16.0 * mL, (k_rerank<0, u64>), cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
                        sb.v[sb.cur], grp, gst, mL, 1, rank, none, (const u32 *)nullptr, none, rr_statusA,
-                       rr_statusB, rrc + 1, (u32 *)nullptr);
+                       rr_statusB, rrc + 1, (u32 *)nullptr, (u32 *)nullptr, 0u);
+            }
+            if (mT) {  // members of a final tie take consecutive slots in text order, the rings dissolve
+                CK(cudaMemsetAsync(tcnt, 0, 16, st));
+                LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round<false>, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, FS, cidx,
+                       n, (u32)k, 1, tcnt);
+                LAUNCH(KC_TUPLE, 4.0 * n + 13.0 * mT, k_tuple_apply, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, n);
             }
             break;
         }
         // ---- one doubling round on both live sets
         ctx->phase = PH_FIX;
-        if (ctx->stats.rounds == 0) ctx->stats.first_live = (long)mS + mL;
+        if (ctx->stats.rounds == 0) ctx->stats.first_live = (long)mS + mL + mT;
         ctx->stats.rounds++;
-        ctx->stats.live_sum += (long)mS + mL;
+        ctx->stats.live_sum += (long)mS + mL + mT;
         sortedS = sortedL = false;
+        CK(cudaMemsetAsync(tcnt, 0, 16, st));
+        if (mT) {
+            // the tuple set first: phase A on old ranks and rings, phase B applies; the rank-ordered sets
+            // gather afterwards (a group is refined as a whole, readers never see it at two depths)
+            if (!linear) {
+                LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round<false>, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, FS, cidx,
+                       n, (u32)k, 0, tcnt);
+            } else {
+                LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round<true>, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, FS, cidx,
+                       n, (u32)k, 0, tcnt);
+            }
+            LAUNCH(KC_TUPLE, 4.0 * n + 13.0 * mT, k_tuple_apply, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, n);
+            tc ^= 1;
+            ctx->stats.tuple_rounds++;
+            ctx->stats.tuple_live_sum += (long)mT;
+        }
         if (mS) {
             // every group fits a warp: gather + in-register ordering, no radix passes; sorted in place
             LAUNCH(KC_LOCAL_SORT, 24.0 * mS, k_local_sort_warp, cdiv((u64)cdiv(mS, 32) * 32, 256), 256, vS, gstS, mS, rank, FS,
@@ -1318,6 +1370,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 10) { g_tune_l2gran = value; return 0; }
     if (key == 11) { g_tune_nomark = value; return 0; }
     if (key == 12) { g_tune_invpath = value; return 0; }
+    if (key == 14) { if (value < 0 || value > 32) return BWTS_B200_EINVAL; g_tune_tmax = value; return 0; }
     if (key == 13) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invq = value; return 0; }
     return BWTS_B200_EINVAL;
 }

@@ -199,6 +199,7 @@ struct RerankCounters {
     u32 keptL;              // live elements compacted into the L stream
     u32 kheadsL;            // groups in the L stream
     u32 pad[5];
+    u32 keptT[RR_SPREAD];   // live elements handed to the tuple set (rings by text position)
 };
 
 struct LiveOut {  // one compaction stream
@@ -224,14 +225,24 @@ struct LiveOut {  // one compaction stream
 // it loaded (s_sink): its input is in registers -- not merely requested -- before any later
 // tile can start writing.  Inputs are read with ld.global.cg (L2, coherent), not through the
 // non-coherent path.  This halves the doubling state: one grp / gst / idx array per set.
-template <bool ROUTE, typename KeyT>
+// MODE 0: no routing, everything kept goes to outS (routing switched off, finalize).
+// MODE 1: L set -- a kept group goes to the tuple set T (at most tmax members, tmax >= 2), to S (at
+//         most 32) or stays in L; sizes are taken from the tile's own head bits, a group that
+//         touches a tile border counts as large.
+// MODE 2: S set -- T or S.
+// Tuple set: the members of a group are linked into a ring by text position, nxtT[idx] = idx of
+// the next member (k_tuple_round); they leave the rank-ordered arrays for good.
+template <int MODE, typename KeyT>
 __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ keys, const u32 *idx,
                                                   const u32 *grp, const u32 *gst, u32 m,
                                                   int finalize, u32 *__restrict__ rank, LiveOut outS,
                                                   const u32 *__restrict__ baseS, LiveOut outL,
                                                   u64 *__restrict__ statusA, u64 *__restrict__ statusB,
-                                                  RerankCounters *__restrict__ ctr, u32 *__restrict__ nr_out)
+                                                  RerankCounters *__restrict__ ctr, u32 *__restrict__ nr_out,
+                                                  u32 *__restrict__ nxtT, u32 tmax)
 {
+    __shared__ u32 s_all[MODE ? RR_TILE : 1];  // idx by tile slot (ring links of the tuple set)
+    __shared__ u32 s_nt[RR_NT / 32];
     __shared__ __align__(16) u32 s_hw[RR_NT / 4 + 4];  // head flags of the tile as a bit array (slot = bit), + the slots after it
     __shared__ u32 s_sink[RR_NT];
     __shared__ u32 s_wh[RR_NT / 32], s_ws[RR_NT / 32], s_wl[RR_NT / 32], s_wg[RR_NT / 32];
@@ -316,6 +327,10 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
 #pragma unroll
         for (int q = 0; q < RR_IPT; q++) x ^= vi[q] ^ vg[q] ^ vs[q];
         s_sink[tid] = x;
+        if (MODE) {
+#pragma unroll
+            for (int q = 0; q < RR_IPT; q++) s_all[tid * RR_IPT + q] = vi[q];
+        }
     }
     s_hb[tid] = (u8)hbits;
     if (tid == RR_NT - 1) s_hb[RR_NT] = (u8)(hbits >> RR_IPT);
@@ -336,15 +351,16 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
         if (pos - hb >= 32) return -1;
         return (int)(x - (pos - hb));
     };
-    auto group_small = [&](u32 hs) -> bool {  // a head among the 32 slots after tile slot hs
+    auto heads_after = [&](u32 hs) -> u32 {  // head bits of the 32 slots after tile slot hs (bit 0 = slot hs + 1)
         const u32 b0 = hs + 1, w = b0 >> 5;
-        return __funnelshift_r(s_hw[w], s_hw[w + 1], b0 & 31) != 0;
+        return __funnelshift_r(s_hw[w], s_hw[w + 1], b0 & 31);
     };
-    u32 kbits = 0, sbits = 0;  // keep, keep-in-S
-    u32 lasth = 0, nS = 0, nL = 0, nG = 0, nhead = 0, nkhead = 0;  // nG: kept heads that go to L
+    u32 kbits = 0, sbits = 0;  // keep in a stream, keep-in-S
+    u32 lasth = 0, nS = 0, nL = 0, nG = 0, nhead = 0, nkhead = 0, nT = 0;  // nG: kept heads that go to L
     {
         // the group my first slot continues: its head is an earlier slot of this tile (or outside it)
-        int route = -1;  // -1 unknown yet, 0 = L, 1 = S
+        int route = -1;  // -1 unknown yet, 0 = L, 1 = S, 2 = T
+        u32 g_hs = 0, g_end = 0;  // tile slots [g_hs, g_end) of the current group when it is routed to T
 #pragma unroll
         for (int q = 0; q < RR_IPT; q++) {
             if ((u32)q < mine) {
@@ -353,19 +369,34 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
                 if (h) {
                     lasth = j0 + q + 1;
                     nhead++;
-                    nkhead += keep;
                     route = -1;
                 }
                 if (keep) {
-                    if (!ROUTE) {
+                    const u32 x = tid * RR_IPT + q;
+                    if (MODE == 0) {
                         route = 1;
                     } else if (route < 0) {
-                        const u32 x = tid * RR_IPT + q;
                         const int hs = h ? (int)x : head_at_or_before(x);
-                        route = (hs >= 0 && group_small((u32)hs)) ? 1 : 0;
+                        route = (MODE == 2) ? 1 : 0;
+                        if (hs >= 0) {
+                            const u32 w32 = heads_after((u32)hs);
+                            if (w32) {  // the group has __ffs(w32) <= 32 members, all inside this tile
+                                const u32 sz = (u32)__ffs(w32);
+                                route = 1;
+                                if (sz <= tmax) { route = 2; g_hs = (u32)hs; g_end = (u32)hs + sz; }
+                            }
+                        }
                     }
-                    kbits |= 1u << q;
-                    if (route == 1) { sbits |= 1u << q; nS++; } else { nL++; nG += h; }
+                    if (route == 2) {
+                        // ring link: the next member in tile order, the head after the last one
+                        nT++;
+                        const u32 nx = (x + 1 < g_end) ? x + 1 : g_hs;
+                        nxtT[vi[q]] = s_all[MODE ? nx : 0];
+                    } else {
+                        nkhead += h;
+                        kbits |= 1u << q;
+                        if (route == 1) { sbits |= 1u << q; nS++; } else { nL++; nG += h; }
+                    }
                 }
             }
         }
@@ -375,15 +406,16 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
     // ---- block-wide scans of (max lasth, sum nS, sum nL)
     const u32 ih = warp_incl_max(lasth), is = warp_incl_sum(nS), il = warp_incl_sum(nL), ig = warp_incl_sum(nG);
     if (lane == 31) { s_wh[warp] = ih; s_ws[warp] = is; s_wl[warp] = il; s_wg[warp] = ig; }
-    const u32 th = warp_sum(nhead), tkh = warp_sum(nkhead);
-    if (lane == 0) { s_nh[warp] = th; s_nk[warp] = tkh; }
+    const u32 th = warp_sum(nhead), tkh = warp_sum(nkhead), tnt = warp_sum(nT);
+    if (lane == 0) { s_nh[warp] = th; s_nk[warp] = tkh; s_nt[warp] = tnt; }
     __syncthreads();
     if (tid == 0) {
-        u32 bh = 0, bk = 0;
+        u32 bh = 0, bk = 0, bt = 0;
 #pragma unroll
-        for (int w = 0; w < RR_NT / 32; w++) { bh += s_nh[w]; bk += s_nk[w]; }
+        for (int w = 0; w < RR_NT / 32; w++) { bh += s_nh[w]; bk += s_nk[w]; bt += s_nt[w]; }
         if (bh) atomicAdd(&ctr->heads[tile % RR_SPREAD], bh);
         if (bk) atomicAdd(&ctr->kheads[tile % RR_SPREAD], bk);
+        if (bt) atomicAdd(&ctr->keptT[tile % RR_SPREAD], bt);
     }
     u32 offh = 0, offs = 0, offl = 0, offg = 0, toth = 0, tots = 0, totl = 0, totg = 0;
 #pragma unroll
@@ -612,6 +644,102 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *idx, const u
             keys_out[lo + gs[h] + pos[h]] = r[h];
             idx_out[lo + gs[h] + pos[h]] = pay[h];
         }
+}
+
+// ---- tuple set: doubling rounds in TEXT order for groups of a few members ---------------------
+// A group of g <= tmax members (pairs and triples of long repeats: 60 % of a DNA text with copied
+// segments stays in such groups for log2(repeat length / k0) rounds) needs neither a sort nor a
+// compaction: with the members linked into a ring by text position (nxt[i] = next member of i's
+// group, NONE32 = i is not in the set),
+//     new rank(i) = rank(i) + #{members m of the ring : rank[succ^k(m)] < rank[succ^k(i)]}
+// and the ring of i's new group = the members with the same key2, in ring order.  The point is
+// locality: neighbours in the text sit in neighbouring rings (the partner of i + 1 is the partner
+// of i, + 1, for as long as the repeat runs), so a warp that sweeps 32 consecutive positions reads
+// nxt[], rank[i + k] and rank[partner + k] as a few contiguous lines -- where the rank-ordered
+// sets pay one DRAM access per gathered rank (20 ms per round for 0.65 G rotations of the 1 GiB
+// DNA input, against the same round here as two streaming sweeps).
+//   k_tuple_round   phase A, reads old ranks and old rings only: dr[i] = the rank increment,
+//                   nxt_out[i] = next member with an equal key2 (NONE32: i became unique).
+//                   finalize: key2 := the text position -- members of a final tie (equal rotations)
+//                   get consecutive slots, every ring dissolves.
+//   k_tuple_apply   phase B: rank[i] += dr[i]; ring entries of resolved positions are cleared in the
+//                   old buffer too (both buffers hold NONE32 for every position outside the set).
+// Phase B completes before the rank-ordered sets gather their key2 of the same round: a group is
+// refined as a whole, so readers never see one group at two depths.
+#define TUPLE_MAX_STEPS 64  // a ring has at most 32 members; corrupt links must not hang the kernel
+
+template <bool LINEAR>
+static __device__ __forceinline__ u32 tuple_key2(const u32 *__restrict__ rank, const u32 *__restrict__ FS,
+                                                 const u32 *__restrict__ cidx, u32 n, u32 k, u32 i)
+{
+    if (LINEAR) {
+        const u64 t = (u64)i + k;
+        return (t < n) ? __ldg(rank + (u32)t) + 1 : 0;
+    }
+    const u32 f = factor_of(FS, cidx, i);
+    const u32 s = __ldg(FS + f), len = __ldg(FS + f + 1) - s;
+    u32 o = i - s;
+    if (len > 1) {
+        o += (k < len) ? k : k % len;
+        if (o >= len) o -= len;
+    }
+    return __ldg(rank + s + o);
+}
+
+// counters[0] += elements still in the set after this round, counters[1] += elements that saw a
+// member with a different key2 (their group split), counters[2] += elements processed
+template <bool LINEAR>
+__global__ void __launch_bounds__(256) k_tuple_round(const u32 *__restrict__ nxt_in, u32 *__restrict__ nxt_out,
+                                                     u8 *__restrict__ dr, const u32 *__restrict__ rank,
+                                                     const u32 *__restrict__ FS, const u32 *__restrict__ cidx, u32 n,
+                                                     u32 k, int finalize, u32 *__restrict__ counters)
+{
+    __shared__ u32 s_cnt[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 stride = gridDim.x * blockDim.x;
+    u32 remain = 0, split = 0, seen = 0;
+    for (u64 i64 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i64 < n; i64 += stride) {
+        const u32 i = (u32)i64;
+        u32 m = ldg_stream_u32(nxt_in + i);
+        if (m == NONE32) continue;
+        seen++;
+        const u32 ki = finalize ? i : tuple_key2<LINEAR>(rank, FS, cidx, n, k, i);
+        u32 less = 0, eqn = NONE32, diff = 0;
+        for (int step = 0; m != i && step < TUPLE_MAX_STEPS; step++) {
+            const u32 km = finalize ? m : tuple_key2<LINEAR>(rank, FS, cidx, n, k, m);
+            less += km < ki;
+            diff |= km != ki;
+            if (km == ki && eqn == NONE32) eqn = m;
+            m = __ldg(nxt_in + m);
+        }
+        if (finalize) eqn = NONE32;
+        nxt_out[i] = eqn;
+        dr[i] = (u8)less;
+        remain += eqn != NONE32;
+        split += diff;
+    }
+    remain = warp_sum(remain); split = warp_sum(split); seen = warp_sum(seen);
+    if (lane_id() == 0) {
+        if (remain) atomicAdd(&s_cnt[0], remain);
+        if (split) atomicAdd(&s_cnt[1], split);
+        if (seen) atomicAdd(&s_cnt[2], seen);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(counters + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_tuple_apply(u32 *__restrict__ nxt_old, const u32 *__restrict__ nxt_new,
+                                                     const u8 *__restrict__ dr, u32 *__restrict__ rank, u32 n)
+{
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u64 i64 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i64 < n; i64 += stride) {
+        const u32 i = (u32)i64;
+        if (nxt_old[i] == NONE32) continue;
+        const u32 d = dr[i];
+        if (d) rank[i] += d;
+        if (nxt_new[i] == NONE32) nxt_old[i] = NONE32;
+    }
 }
 
 // ---- CTA-local sort: one doubling round of a live set whose groups fit one CTA ------------------

@@ -36,9 +36,9 @@ static void print_timings(bwts_b200_ctx *ctx)
 	}
 	if (s.direction == 0)
 		fprintf(stderr, "Factors: %10ld; longest: %10ld; alphabet bits: %d; initial depth: %d; live after initial sort: %10ld; "
-		        "doubling rounds: %d (warp-local %d, CTA-local %d); radix passes: %d; live sum: %ld; workspace bytes/byte: %.1f\n",
+		        "doubling rounds: %d (warp-local %d, CTA-local %d, tuple set %d); radix passes: %d; live sum: %ld; workspace bytes/byte: %.1f\n",
 		        s.factors, s.longest_factor, s.alphabet_bits, s.initial_depth, s.first_live, s.rounds, s.local_rounds,
-		        s.cta_rounds, s.radix_passes, s.live_sum, s.len ? (double)s.arena_bytes / (double)s.len : 0.0);
+		        s.cta_rounds, s.tuple_rounds, s.radix_passes, s.live_sum, s.len ? (double)s.arena_bytes / (double)s.len : 0.0);
 	else
 		fprintf(stderr, "Cycles: %10ld; sublists: %10ld; unreached: %10ld; workspace bytes/byte: %.1f\n", s.factors,
 		        s.splitters, s.unreached, s.len ? (double)s.arena_bytes / (double)s.len : 0.0);

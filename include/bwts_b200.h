@@ -24,8 +24,8 @@
  * fallback: without a CUDA device every transform fails with BWTS_B200_ENODEV.
  *
  * Limits: 1 <= len < 2^31 per block, the reference's own range (`int` / `saidx_t`,
- * mk_bwts_sa.c:26-27, unbwts.c:12-13).  The device workspace is 62 bytes per input byte (+ 64 MiB,
- * + 2 per byte for the host-buffer calls): 2 GiB blocks need ~137 GB of the B200's 180 GB.
+ * mk_bwts_sa.c:26-27, unbwts.c:12-13).  The device workspace is 71 bytes per input byte (+ 64 MiB,
+ * + 2 per byte for the host-buffer calls): 2 GiB blocks need ~157 GB of the B200's 192 GB.
  */
 #ifndef BWTS_B200_H
 #define BWTS_B200_H
@@ -122,6 +122,8 @@ typedef struct {
     double phase_ms[BWTS_B200_NPHASE];
     long   arena_bytes;         /* device workspace held by the context after this transform */
     long   first_live;          /* forward: rotations still tied after the initial sort      */
+    int    tuple_rounds;        /* forward: rounds in which the text-ordered tuple set ran   */
+    long   tuple_live_sum;      /* forward: sum over those rounds of its members             */
 } bwts_b200_stats;
 
 int bwts_b200_get_stats(const bwts_b200_ctx *ctx, bwts_b200_stats *out);
@@ -144,7 +146,10 @@ const char *bwts_b200_version(void);
  * the initial packed key (8..64), 7 = binned rank scatter of the first re-rank (1 = never,
  * 2 = always; default: inputs of 4 Mi bytes and more), 8 = never sort the large-group set
  * CTA-locally (1), 9 = emit through rank windows (1) or binned by rank region (2; default:
- * binned from 512 Mi bytes).  value 0 = default.                                        */
+ * binned from 512 Mi bytes), 10 = cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured: no
+ * effect), 12 = inverse through two read-only walks (1) instead of the staged single walk, 13 =
+ * sublists per warp of the staged walk, 14 = largest group the text-ordered tuple set takes (1 =
+ * set switched off, 2..32; default 8).  value 0 = default.                               */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

@@ -83,7 +83,10 @@ def lyndon_starts_chunked(T, B):
     return np.flatnonzero(flags)
 
 
-def forward(T, chunk=16, trace=None):
+def forward(T, chunk=16, trace=None, tmax=0):
+    """tmax > 0: groups of at most tmax members leave the rank-ordered live array for the
+    text-ordered tuple set (forward.cuh: k_tuple_round / k_tuple_apply): members linked in a ring
+    by text position, new rank = old rank + number of ring members with a smaller key2."""
     T = np.frombuffer(bytes(T), dtype=np.uint8)
     n = len(T)
     FS = np.append(lyndon_starts_chunked(T, chunk), n).astype(np.int64)
@@ -117,6 +120,9 @@ def forward(T, chunk=16, trace=None):
     m = n
     k = k0
     rounds = 0
+    NONE = -1
+    ring = np.full(n, NONE, dtype=np.int64)   # tuple set: next member of my group, by text position
+    tstats = dict(entered=0, t_rounds=0)
 
     def rerank(skey, idx, grp, gst, m, finalize=False):
         j = np.arange(m)
@@ -131,33 +137,83 @@ def forward(T, chunk=16, trace=None):
         newrank = grp[:m] + (jh - gst[:m])
         changed = newrank != grp[:m]
         rank[idx[:m][changed]] = newrank[changed]
-        c = np.cumsum(keep) - keep       # exclusive
-        nidx = idx[:m][keep]
-        ngrp = newrank[keep]
-        ngst = (c - (j - jh))[keep]
         nheads = int(head.sum())
-        return nidx, ngrp, ngst, int(keep.sum()), nheads
+        # route: kept groups of at most tmax members go to the tuple set
+        heads_pos = np.flatnonzero(head)
+        sizes = np.diff(np.append(heads_pos, m))
+        size_of = np.repeat(sizes, sizes)
+        to_t = keep & (size_of <= tmax) if (tmax and not finalize) else np.zeros(m, dtype=bool)
+        for h, sz in zip(heads_pos, sizes):
+            if sz >= 2 and to_t[h]:
+                members = idx[h:h + sz]
+                ring[members] = np.roll(members, -1)
+                tstats["entered"] += int(sz)
+        stay = keep & ~to_t
+        c = np.cumsum(stay) - stay       # exclusive
+        nidx = idx[:m][stay]
+        ngrp = newrank[stay]
+        # offset of the group start in the compacted array: members of a group that stays are contiguous
+        first_of_group = np.repeat(heads_pos, sizes)
+        ngst = c[first_of_group][stay]
+        kheads = int((head & stay).sum())
+        return nidx, ngrp, ngst, int(stay.sum()), nheads, kheads
 
-    old_groups = 1
-    nidx, ngrp, ngst, m2, nheads = rerank(skey, idx, grp, gst, m)
+    def tuple_round(k, finalize=False):
+        """phase A (k_tuple_round) computes on the old ranks / rings, phase B (k_tuple_apply) applies"""
+        live = np.flatnonzero(ring != NONE)
+        new_ring = ring.copy()
+        dr = np.zeros(n, dtype=np.int64)
+        split = False
+        for i in live:
+            ki = i if finalize else rank[succ_k(i, k)]
+            less, eqn, mm = 0, NONE, ring[i]
+            while mm != i:
+                km = mm if finalize else rank[succ_k(mm, k)]
+                less += km < ki
+                split |= bool(km != ki)
+                if km == ki and eqn == NONE:
+                    eqn = mm
+                mm = ring[mm]
+            dr[i] = less
+            new_ring[i] = NONE if finalize else eqn
+        rank[live] += dr[live]
+        ring[:] = new_ring
+        return split, int((ring != NONE).sum())
+
+    nidx, ngrp, ngst, m2, nheads, kheads = rerank(skey, idx, grp, gst, m)
     idx, grp, gst, m = nidx, ngrp, ngst, m2
-    while m > 0 and k < 2 * lmax:
-        groups_before = int((gst[:m] == np.arange(m)).sum())
-        key2 = rank[succ_k(idx[:m], k)]
-        comp = gst[:m] * (n + 1) + key2
-        perm = np.argsort(comp, kind="stable")
-        skey = comp[perm]
-        idx = idx[:m][perm]
-        nidx, ngrp, ngst, m2, nheads = rerank(skey, idx, grp, gst, m)
+    mt = int((ring != NONE).sum())
+    while m + mt > 0 and k < 2 * lmax:
+        groups_before = kheads
+        split_t = False
+        if mt:
+            split_t, mt = tuple_round(k)
+            tstats["t_rounds"] += 1
+        nheads = groups_before
+        if m:
+            key2 = rank_before_t = None
+        if m:
+            # the rank-ordered sets gather AFTER the tuple set applied its new ranks (kernel order in
+            # forward_core): groups are refined as a whole, so mixed depths are consistent
+            key2 = rank[succ_k(idx[:m], k)]
+            comp = gst[:m] * (n + 1) + key2
+            perm = np.argsort(comp, kind="stable")
+            skey = comp[perm]
+            idx = idx[:m][perm]
+            nidx, ngrp, ngst, m2, nheads, kheads2 = rerank(skey, idx, grp, gst, m)
         rounds += 1
         k *= 2
-        if nheads == groups_before:     # fixpoint: nothing split
+        if nheads == groups_before and not split_t:     # fixpoint: nothing split anywhere
             break
-        idx, grp, gst, m = nidx, ngrp, ngst, m2
+        if m:
+            idx, grp, gst, m, kheads = nidx, ngrp, ngst, m2, kheads2
+        mt = int((ring != NONE).sum())
     if m > 0:
         rerank(None, idx, grp, gst, m, finalize=True)
+    if (ring != NONE).any():
+        tuple_round(k, finalize=True)
     if trace is not None:
-        trace.update(rounds=rounds, k=k, factors=len(FS) - 1, bits=bits, k0=k0)
+        trace.update(rounds=rounds, k=k, factors=len(FS) - 1, bits=bits, k0=k0, **tstats)
     # emit (forward.cu: k_emit / k_emit_heads)
     out = np.zeros(n, dtype=np.uint8)
     prevpos = np.arange(n) - 1

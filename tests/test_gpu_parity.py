@@ -450,7 +450,7 @@ def test_timings_use_the_reference_phase_labels(gen, tmp_path):
     assert m, diag[0]
     factors, longest, bits, depth, live0, rounds = (int(m.group(i)) for i in range(1, 7))
     assert factors >= 1 and 1 <= longest <= len(x) and bits == 2 and depth == 32 and rounds >= 1 and live0 <= len(x)
-    assert int(m.group(10)) >= live0 > 0
+    assert int(m.group(11)) >= live0 > 0
     # the inverse tool: additive labels, same format
     p = subprocess.run([str(bindir / "unbwts"), str(dst), str(tmp_path / "back")], capture_output=True, text=True, env=env)
     assert p.returncode == 0, p.stderr
@@ -487,6 +487,37 @@ def test_local_sort_path_and_radix_only_path_agree(bwts, ctx, oracle, gen):
         b = ctx.forward_host(x)
         assert a == want and b == want
         assert ra == 0
+
+
+def test_tuple_set_sizes_agree(bwts, ctx, oracle, gen):
+    """the text-ordered tuple set (rings by text position, k_tuple_round / k_tuple_apply) switched off
+    (tune 14 = 1), taking pairs only (2), its default (8) and everything the small-group set would take
+    (32): all equal the oracle; suffix arrays (linear successor) through the same paths"""
+    rng = np.random.default_rng(11)
+    base = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=40_000))
+    copies = base + b"T" + base[5_000:30_000] + b"G" + base + base[100:20_000] + b"A" + base[5_000:30_000]
+    cases = [gen.make("dna", 81, 2_500_000), gen.make("text", 82, 1_200_000), gen.make("tiled", 83, 1_100_000), copies,
+             helpers.families(60_000)["ww"], helpers.families(60_000)["runs"], helpers.families(4097)["abab"],
+             helpers.fibonacci_word(150_000), b"a" * 5000, gen.make("dna", 84, 4609)]
+    try:
+        for x in cases:
+            want = oracle.forward(x)
+            seen = {}
+            for tmax in (1, 2, 0, 32):
+                bwts.tune(14, tmax)
+                assert ctx.forward_host(x) == want, (len(x), tmax)
+                seen[tmax] = ctx.stats()["tuple_rounds"]
+            assert seen[1] == 0
+        bwts.tune(14, 0)
+        ctx.forward_host(cases[0])
+        st = ctx.stats()
+        assert st["tuple_rounds"] >= 3 and st["tuple_live_sum"] > len(cases[0]), "the DNA input must use the tuple set"
+        for tmax in (1, 2, 32):
+            bwts.tune(14, tmax)
+            for x in (cases[3], cases[0][:300_000], helpers.fibonacci_word(50_000)):
+                assert np.array_equal(bwts.suffix_array(x), oracle.suffix_array(x)), tmax
+    finally:
+        bwts.tune(14, 0)
 
 
 def test_lyndon_suffix_sort_fallback(bwts, ctx, oracle, gen):

@@ -31,6 +31,24 @@ def test_doubling_forward(oracle):
         assert model.forward(x, chunk=8) == oracle.forward(x), name
 
 
+def test_doubling_forward_with_tuple_set(oracle):
+    """small groups leave the rank-ordered arrays for the text-ordered tuple set (rings by text
+    position, rank += number of ring members with a smaller key2)"""
+    used = 0
+    rng = np.random.default_rng(3)
+    cases = _cases()
+    for n in (400, 900):
+        base = rng.integers(0, 4, size=n // 3, dtype=np.uint8)
+        cases.append((f"copies_{n}", bytes(np.concatenate([base, rng.integers(0, 4, size=7, dtype=np.uint8), base, base[: n // 5]]) + 65)))
+    for name, x in cases:
+        want = oracle.forward(x)
+        for tmax in (2, 8, 1000):
+            tr = {}
+            assert model.forward(x, chunk=8, tmax=tmax, trace=tr) == want, (name, tmax)
+            used += tr["entered"]
+    assert used > 1000
+
+
 def test_splitter_inverse(oracle):
     for name, x in _cases():
         for shift in (26, 30, 31):
