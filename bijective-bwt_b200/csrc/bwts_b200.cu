@@ -49,6 +49,8 @@ static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied whe
 static long g_tune_tmax = 0;       // tuple set: largest group it takes (0 = 8, 1 = set switched off, 2..32)
 static long g_tune_invpath = 0;    // inverse: 0 = staged single walk (default), 1 = two read-only walks (round 1)
 static long g_tune_invq = 0;       // inverse staged walk: sublists per warp (0 = auto: one full wave of warps)
+static long g_tune_invmark = 0;    // inverse staged walk: 0 = one count per 128 elements, 1 = one bit per element
+static long g_tune_invbudget = 0;  // inverse fallback walks: step budget per attempt (0 = 32 n)
 static long g_tune_nomark = 0;     // TIMING EXPERIMENT ONLY: inverse first walk without visited marks (wrong output when a cycle has no splitter)
 
 static void apply_device_limits()
@@ -317,7 +319,10 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     u32 *kS = arena_take<u32>(ctx, n);   // S set: key2 of the last warp-local sort
     u32 *vS = arena_take<u32>(ctx, n), *grpS = arena_take<u32>(ctx, n), *gstS = arena_take<u32>(ctx, n);
     // tuple set T (k_tuple_round): ring links by text position, double-buffered, + the rank increments
-    const u32 tmax = g_tune_local ? 1u : (g_tune_tmax == 0 ? 8u : (u32)g_tune_tmax);  // 1 = switched off
+    // tune 14: 0 = groups of up to 8, switched on by what the first small-group round finds (below); 1 = off;
+    // 2..32 = that size, on from the first re-rank (tests)
+    const u32 tmax = g_tune_local ? 1u : (g_tune_tmax == 0 ? 8u : (u32)g_tune_tmax);
+    bool t_on = !g_tune_local && g_tune_tmax >= 2, t_decided = t_on || tmax < 2;
     u32 *nxtT[2] = {nullptr, nullptr};
     u8 *drT = nullptr;
     if (tmax >= 2) {
@@ -418,7 +423,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     if (rc) return rc;
 
     CK(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
-    if (tmax >= 2) {  // every position starts outside the tuple set, in both buffers
+    if (t_on) {  // every position starts outside the tuple set, in both buffers
         CK(cudaMemsetAsync(nxtT[0], 0xff, (size_t)n * 4, st));
         CK(cudaMemsetAsync(nxtT[1], 0xff, (size_t)n * 4, st));
     }
@@ -443,7 +448,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         if (mS && sortedS) {
             CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
             CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
-            if (tmax >= 2) {
+            if (t_on) {
                 LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<2, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
                        (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, nxtT[tc], tmax);
             } else {
@@ -469,7 +474,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             } else {
                 LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<1, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL,
-                       rr_statusA, rr_statusB, rrc + 1, nr_out, tmax >= 2 ? nxtT[tc] : (u32 *)nullptr, tmax >= 2 ? tmax : 0u);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out, t_on ? nxtT[tc] : (u32 *)nullptr, t_on ? tmax : 0u);
             }
         }
         if (mL && sortedL && first && use_binned_scatter(n, kb)) {
@@ -578,10 +583,26 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         }
         if (mS) {
             // every group fits a warp: gather + in-register ordering, no radix passes; sorted in place
+            // The first small-group round also measures how many of its rotations stay tied: where most do,
+            // the ties come from long repeats (DNA with copied segments: 98 %), neighbours in the text sit
+            // in neighbouring groups and the tuple set's text-order sweeps beat one gather per rotation;
+            // where few do (text: the ties end within a round or two) the set would only add random traffic.
+            u32 *surv = (!t_decided && mS >= (n >> 5)) ? tcnt + 4 : (u32 *)nullptr;
+            if (surv) CK(cudaMemsetAsync(surv, 0, 8, st));
             LAUNCH(KC_LOCAL_SORT, 24.0 * mS, k_local_sort_warp, cdiv((u64)cdiv(mS, 32) * 32, 256), 256, vS, gstS, mS, rank, FS,
-                   cidx, (u32)k, kb, n, linear, kS, vS);
+                   cidx, (u32)k, kb, n, linear, kS, vS, surv);
             ctx->stats.local_rounds++;
             sortedS = true;
+            if (surv) {
+                rc = readback(ctx, st, surv, 8);
+                if (rc) return rc;
+                t_decided = true;
+                if (ctx->h_small[0] && 2ull * ctx->h_small[1] >= ctx->h_small[0]) {
+                    t_on = true;
+                    CK(cudaMemsetAsync(nxtT[0], 0xff, (size_t)n * 4, st));
+                    CK(cudaMemsetAsync(nxtT[1], 0xff, (size_t)n * 4, st));
+                }
+            }
         }
         if (mL) {
             // groups that fit one CTA: gather + bitonic network in shared memory, no radix passes
@@ -680,14 +701,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
 }
 
 // ---- inverse -----------------------------------------------------------------------------------
-static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cudaStream_t st)
+// One attempt with the splitter hash h.  budget_k: step budget (in units of 1024 steps) of the
+// fallback walks over cycles without splitters, 0 = unbounded; *over is set when it ran out.
+static int inverse_attempt(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cudaStream_t st, SplHash h, u32 budget_k,
+                           bool *over)
 {
-    int rc = arena_reserve(ctx, workspace_bytes(n));
-    if (rc) return rc;
-    ctx->arena_used = 0;
-    if (ctx->io_in && ctx->io_in == dB) ctx->arena_used = ((size_t)2 * ctx->io_bytes + 511) & ~(size_t)255;
-
-    const u32 shift = g_tune_spl_shift ? (u32)g_tune_spl_shift : 26u;
+    *over = false;
+    const u32 shift = h.shift;
     const u32 ntiles = cdiv(n, INV_TILE), nchunks = cdiv(ntiles, INV_CHUNK);
     const u32 nst = cdiv(n, SP_TILE), nsc = cdiv(n, SC_TILE);
 
@@ -695,12 +715,15 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     u32 *chunksum = arena_take<u32>(ctx, (size_t)nchunks * 256);
     u32 *prev = arena_take<u32>(ctx, n);
     const bool staged = g_tune_invpath == 0;
+    const bool count_marks = staged && g_tune_invmark == 0;  // per-128 counts instead of one bit per element
     u32 *sid = staged ? (u32 *)nullptr : arena_take<u32>(ctx, n);  // two-walk path only (sparse element -> sublist map)
     u32 *len_at_min = arena_take<u32>(ctx, n);
     u32 *off = arena_take<u32>(ctx, n);
     uint2 *cyc = arena_take<uint2>(ctx, n);
     u32 *tilecnt = arena_take<u32>(ctx, max(nst, nsc) + 1);
-    u32 *small = arena_take<u32>(ctx, 512);  // [0] ns, [2] visited total, [4] unreached, [6] cycles, [8] scan total, [64..320] C
+    // [0] ns, [2] reached, [4] unreached handled, [5] fallback steps / 1024, [6] cycles, [8] scan total,
+    // [10] deficient blocks, [12] budget exhausted, [64..320] C
+    u32 *small = arena_take<u32>(ctx, 512);
     if (!tilehist || !chunksum || !prev || (!staged && !sid) || !len_at_min || !off || !cyc || !tilecnt || !small)
         return BWTS_B200_EINTERNAL;
     u32 *Ctab = small + 64;
@@ -718,9 +741,9 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     // -- splitters
     ctx->phase = 2;
     CK(cudaMemsetAsync(len_at_min, 0, (size_t)n * 4, st));
-    LAUNCH(KC_INV_WALK, 0, k_inv_spl_count, nst, 256, n, shift, tilecnt);
+    LAUNCH(KC_INV_WALK, 0, k_inv_spl_count, nst, 256, n, h, tilecnt);
     LAUNCH(KC_INV_SCAN, 8.0 * nst, k_scan_excl_u32_block, 1, 1024, tilecnt, tilecnt, nst, small + 0);
-    rc = readback(ctx, st, small, 4);
+    int rc = readback(ctx, st, small, 4);
     if (rc) return rc;
     const u32 ns = ctx->h_small[0];
     if (ns < 1 || ns > n) return BWTS_B200_EINTERNAL;
@@ -742,21 +765,25 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
         stage = arena_take<u8>(ctx, (size_t)ns * slot);
         if (!blkoff || !nxt || !cont || !stage) return BWTS_B200_EINTERNAL;
     }
-    LAUNCH(KC_INV_WALK, 8.0 * ns, k_inv_spl_write, nst, 256, n, shift, tilecnt, spl, staged ? (u32 *)nullptr : sid, blkoff);
-    // first walk: 4 B read per element, one visited bit set per element (bitmap lives in L2)
-    u32 *visited = arena_take<u32>(ctx, (size_t)(n >> 5) + 2);
-    if (!visited) return BWTS_B200_EINTERNAL;
-    CK(cudaMemsetAsync(visited, 0, ((size_t)(n >> 5) + 2) * 4, st));
+    LAUNCH(KC_INV_WALK, 8.0 * ns, k_inv_spl_write, nst, 256, n, h, tilecnt, spl, staged ? (u32 *)nullptr : sid, blkoff);
+    // who gets reached: one bit per element, or (staged path) one 8-bit count per 128 elements
+    const size_t vwords = (size_t)(n >> 5) + 2, cwords = (size_t)(n >> 9) + 2;
+    u32 *visited = arena_take<u32>(ctx, vwords);
+    u32 *vcnt = count_marks ? arena_take<u32>(ctx, cwords) : (u32 *)nullptr;
+    if (!visited || (count_marks && !vcnt)) return BWTS_B200_EINTERNAL;
+    if (count_marks) CK(cudaMemsetAsync(vcnt, 0, cwords * 4, st));
+    else CK(cudaMemsetAsync(visited, 0, vwords * 4, st));
     if (staged) {
         // one full wave of warps (64 per SM), each owning a contiguous range of Q sublists
         const u32 wave = (u32)ctx->sm_count * 64u;
         u32 Q = g_tune_invq > 0 ? (u32)g_tune_invq : max(64u, cdiv(ns, wave));
         const u32 nwarps = cdiv(ns, Q);
-        LAUNCH(KC_INV_WALK, 5.0 * n, k_inv_walk_stage, cdiv(nwarps, 8), 256, prev, shift, spl, ns, Q, Ctab, nxt, wlen, minfo,
-               stage, slot, cont, g_tune_nomark ? (u32 *)nullptr : visited, small + 2);
-        LAUNCH(KC_INV_WALK, 20.0 * ns, k_inv_resolve_next, cdiv(ns, 256), 256, nxt, minfo, blkoff, shift, ns, jm[0]);
+        LAUNCH(KC_INV_WALK, 5.0 * n, k_inv_walk_stage, cdiv(nwarps, 8), 256, prev, h, spl, ns, Q, Ctab, nxt, wlen, minfo,
+               stage, slot, cont, (g_tune_nomark || count_marks) ? (u32 *)nullptr : visited, g_tune_nomark ? (u32 *)nullptr : vcnt,
+               small + 2);
+        LAUNCH(KC_INV_WALK, 20.0 * ns, k_inv_resolve_next, cdiv(ns, 256), 256, nxt, minfo, blkoff, h, ns, jm[0]);
     } else {
-        LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, shift, spl, ns, sid, jm[0], wlen, minfo,
+        LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk, cdiv(ns, 128), 128, prev, h, spl, ns, sid, jm[0], wlen, minfo,
                g_tune_nomark ? (u32 *)nullptr : visited, small + 2);
     }
 
@@ -785,11 +812,33 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     const u32 reached = ctx->h_small[0];
     uint2 *urec = nullptr;
     const u32 nwords = cdiv(n, 32);
-    if (reached != n) {
+    const u32 bk = budget_k ? budget_k : 0xffffffffu;
+    if (reached != n && !g_tune_nomark) {
+        ctx->phase = 2;
+        if (count_marks) {
+            // the blocks of 128 whose count is short hold the unreached elements: few blocks (the usual case:
+            // a handful of short last factors) -> test their elements one by one; many -> mark exactly
+            const u32 cap = max(4096u, n >> 13);
+            u32 *deflist = arena_take<u32>(ctx, cap);
+            if (!deflist) return BWTS_B200_EINTERNAL;
+            LAUNCH(KC_INV_WALK, (double)(n >> 7), k_inv_find_deficient, cdiv(cdiv(n, 128), 256), 256, vcnt, n, deflist, cap, small + 10);
+            rc = readback(ctx, st, small + 10, 4);
+            if (rc) return rc;
+            const u32 ndef = ctx->h_small[0];
+            if (ndef <= cap) {
+                CK(cudaMemsetAsync(visited, 0xff, vwords * 4, st));
+                LAUNCH(KC_INV_WALK, 512.0 * ndef, k_inv_verify_candidates, cdiv((u64)ndef * 128, 128), 128, prev, n, h, deflist, ndef,
+                       visited, small + 4, bk, small + 12);
+            } else {
+                CK(cudaMemsetAsync(visited, 0, vwords * 4, st));
+                LAUNCH(KC_INV_WALK, 4.0 * n, k_inv_walk_mark, cdiv(ns, 128), 128, prev, h, spl, ns, visited);
+            }
+        }
         urec = arena_take<uint2>(ctx, n);
         if (!urec) return BWTS_B200_EINTERNAL;
         LAUNCH(KC_INV_WALK, 12.0 * (n - reached), k_inv_self_walk, cdiv(nwords, 256), 256, prev, n, visited, urec,
-               len_at_min, small + 4);
+               len_at_min, small + 4, bk, small + 12);
+        ctx->phase = 3;
     }
 
     // -- offsets of the cycles, in order of ascending smallest index
@@ -802,21 +851,62 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     LAUNCH(KC_INV_PLACE, 44.0 * ns, k_inv_spl_record, gs, 256, jmR, pv[pc], cyc, off, ns, srec);
     if (staged) {
         LAUNCH(KC_INV_PLACE, 2.0 * n + 20.0 * ns, k_inv_place_copy, cdiv(ns, 8), 256, stage, wlen, srec, ns, n, slot, d_out);
-        LAUNCH(KC_INV_PLACE, 8.0 * ns, k_inv_walk_tail, cdiv(ns, 128), 128, prev, n, shift, wlen, cont, ns, slot, srec, Ctab, d_out);
+        LAUNCH(KC_INV_PLACE, 8.0 * ns, k_inv_walk_tail, cdiv(ns, 128), 128, prev, n, h, wlen, cont, ns, slot, srec, Ctab, d_out);
     } else {
-        LAUNCH(KC_INV_PLACE, 5.0 * n, k_inv_walk_place, cdiv(ns, 128), 128, prev, n, shift, spl, ns, srec, Ctab, d_out);
+        LAUNCH(KC_INV_PLACE, 5.0 * n, k_inv_walk_place, cdiv(ns, 128), 128, prev, n, h, spl, ns, srec, Ctab, d_out);
     }
     if (urec)
         LAUNCH(KC_INV_PLACE, 14.0 * (n - reached), k_inv_place_unreached, cdiv(nwords, 256), 256, dB, n, visited, urec,
                off, d_out);
 
-    rc = readback(ctx, st, small, 40);
+    rc = readback(ctx, st, small, 56);
     if (rc) return rc;
+    if (ctx->h_small[12]) { *over = true; return 0; }      // the fallback ran out of budget: the caller tries another hash
+    if (g_tune_nomark) return 0;                            // timing experiment, the output is not checked
     if (ctx->h_small[8] != n) return BWTS_B200_EINTERNAL;  // cycle lengths must add up to n
     ctx->stats.splitters = ns;
     ctx->stats.unreached = ctx->h_small[4];
     ctx->stats.factors = ctx->h_small[6];
     return 0;
+}
+
+static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cudaStream_t st)
+{
+    int rc = arena_reserve(ctx, workspace_bytes(n));
+    if (rc) return rc;
+    // A cycle that holds no splitter is ranked by its own members walking it: L steps each, L^2 per
+    // cycle.  With random-looking hashing such cycles are short (a cycle of L elements is missed with
+    // probability e^(-L / 64): at most ~24 steps per element on any input), so 32 n steps are a
+    // generous budget; an input built against the public hash exceeds it and the inverse starts
+    // again with another multiplier -- and four times the splitter density where the workspace has
+    // room for it -- the last attempt unbounded.
+    static const u32 muls[4] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu};
+    u32 shift = g_tune_spl_shift ? (u32)g_tune_spl_shift : 26u;
+    ctx->stats.inverse_attempts = 0;
+    for (int a = 0; a < 4; a++) {
+        ctx->arena_used = 0;
+        if (ctx->io_in && ctx->io_in == dB) ctx->arena_used = ((size_t)2 * ctx->io_bytes + 511) & ~(size_t)255;
+        const u64 steps = g_tune_invbudget > 0 ? (u64)g_tune_invbudget : 32ull * n;
+        u64 bk64 = steps >> 10;
+        if (bk64 < 1) bk64 = 1;
+        if (bk64 > 0xfffffffeull) bk64 = 0xfffffffeull;
+        const u32 budget_k = (a == 3) ? 0u : (u32)bk64;
+        bool over = false;
+        ctx->stats.inverse_attempts++;
+        rc = inverse_attempt(ctx, dB, n, d_out, st, SplHash{muls[a], shift}, budget_k, &over);
+        if (rc || !over) return rc;
+        if (shift < 30) {
+            // denser splitters if ~(80 + slot) bytes per sublist fit behind the per-element arrays (~33 n)
+            const u32 s2 = shift + 2;
+            const u64 ns2 = ((u64)n >> (32 - s2)) + 1024;
+            u64 slot2 = (4ull << (32 - s2)) & ~31ull;
+            if (slot2 < 32) slot2 = 32;
+            if (slot2 > INV_SLOT_MAX) slot2 = INV_SLOT_MAX;
+            const u64 need = 34ull * n + ns2 * (80 + slot2) * 5 / 4 + (ctx->io_in ? 2 * (u64)ctx->io_bytes : 0) + (16u << 20);
+            if (need <= ctx->arena_bytes) shift = s2;
+        }
+    }
+    return BWTS_B200_EINTERNAL;
 }
 
 // ---- contexts -------------------------------------------------------------------------------------
@@ -1371,6 +1461,8 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 11) { g_tune_nomark = value; return 0; }
     if (key == 12) { g_tune_invpath = value; return 0; }
     if (key == 14) { if (value < 0 || value > 32) return BWTS_B200_EINVAL; g_tune_tmax = value; return 0; }
+    if (key == 15) { g_tune_invmark = value; return 0; }
+    if (key == 16) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invbudget = value; return 0; }
     if (key == 13) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invq = value; return 0; }
     return BWTS_B200_EINVAL;
 }

@@ -568,11 +568,26 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *idx, const u
                                                          u32 m, const u32 *__restrict__ rank,
                                                          const u32 *__restrict__ FS, const u32 *__restrict__ cidx,
                                                          u32 k, u32 kb, u32 n, int linear,
-                                                         u32 *__restrict__ keys_out, u32 *idx_out)
+                                                         u32 *__restrict__ keys_out, u32 *idx_out,
+                                                         u32 *__restrict__ surv)
 {
+    // surv != nullptr: every 16th block reports (slots, slots still tied with a member of their group)
+    // -- the host's estimate of how long the repeats behind the small groups are (tuple set on / off)
+    __shared__ u32 s_surv[2];
+    const bool sample = surv != nullptr && (blockIdx.x & 15u) == 0;
+    if (sample) {
+        if (threadIdx.x < 2) s_surv[threadIdx.x] = 0;
+        __syncthreads();
+    }
     const u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u32 lane = lane_id();
-    if ((u64)w * 32 >= m) return;
+    if ((u64)w * 32 >= m) {
+        if (sample) {  // keep the block's barrier count
+            __syncthreads();
+            if (threadIdx.x < 2 && s_surv[threadIdx.x]) atomicAdd(surv + threadIdx.x, s_surv[threadIdx.x]);
+        }
+        return;
+    }
     const u32 lo = __ldg(gst + w * 32);
     const u32 hi = ((u64)(w + 1) * 32 < m) ? __ldg(gst + (w + 1) * 32) : m;
     const u32 cnt = hi - lo;  // 1 .. 63
@@ -626,7 +641,7 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *idx, const u
         if (s < cnt) maxlen = max(maxlen, ge[h] - gs[h]);
     }
     maxlen = warp_max(maxlen);
-    u32 pos[2] = {0, 0};
+    u32 pos[2] = {0, 0}, tied[2] = {0, 0};
     for (u32 o = 0; o < maxlen; o++) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -636,7 +651,13 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *idx, const u
             const u32 other = (t & 32) ? b : a;
             const u32 me = lane + 32 * h;
             pos[h] += (t < ge[h]) && ((other < r[h]) || (other == r[h] && t < me));
+            tied[h] |= (t < ge[h]) && (other == r[h]) && (t != me);
         }
+    }
+    if (sample) {
+        const u32 c = warp_sum((u32)(lane < cnt) + (u32)(lane + 32 < cnt));
+        const u32 t = warp_sum(((lane < cnt) ? tied[0] : 0u) + ((lane + 32 < cnt) ? tied[1] : 0u));
+        if (lane == 0) { atomicAdd(&s_surv[0], c); atomicAdd(&s_surv[1], t); }
     }
 #pragma unroll
     for (int h = 0; h < 2; h++)
@@ -644,6 +665,10 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *idx, const u
             keys_out[lo + gs[h] + pos[h]] = r[h];
             idx_out[lo + gs[h] + pos[h]] = pay[h];
         }
+    if (sample) {
+        __syncthreads();
+        if (threadIdx.x < 2 && s_surv[threadIdx.x]) atomicAdd(surv + threadIdx.x, s_surv[threadIdx.x]);
+    }
 }
 
 // ---- tuple set: doubling rounds in TEXT order for groups of a few members ---------------------
@@ -686,8 +711,33 @@ static __device__ __forceinline__ u32 tuple_key2(const u32 *__restrict__ rank, c
     return __ldg(rank + s + o);
 }
 
+// One ring member's share of phase A: walks the ring from m (the member after i), key2 of i given.
+template <bool LINEAR>
+static __device__ __forceinline__ void tuple_walk(const u32 *__restrict__ nxt_in, const u32 *__restrict__ rank,
+                                                  const u32 *__restrict__ FS, const u32 *__restrict__ cidx, u32 n, u32 k,
+                                                  int finalize, u32 i, u32 ki, u32 m, u32 km, u32 mn, u32 &less, u32 &eqn,
+                                                  u32 &diff)
+{
+    // (m, km, mn) = first member after i, its key2 and its successor, already loaded by the caller
+    less = km < ki;
+    diff = km != ki;
+    eqn = (km == ki) ? m : NONE32;
+    m = mn;
+    for (int step = 0; m != i && step < TUPLE_MAX_STEPS; step++) {
+        const u32 kq = finalize ? m : tuple_key2<LINEAR>(rank, FS, cidx, n, k, m);
+        less += kq < ki;
+        diff |= kq != ki;
+        if (kq == ki && eqn == NONE32) eqn = m;
+        m = __ldg(nxt_in + m);
+    }
+}
+
 // counters[0] += elements still in the set after this round, counters[1] += elements that saw a
-// member with a different key2 (their group split), counters[2] += elements processed
+// member with a different key2 (their group split), counters[2] += elements processed.
+// A thread owns 4 consecutive positions: one 16-byte load tells it whether any of them is in the
+// set (the sweep over the n positions costs 4 bytes each), and the loads of the four first ring
+// steps -- key2 of the position, key2 and successor of its ring neighbour -- are all issued before
+// the first of them is used (the kernel is bound by memory latency, not by bytes).
 template <bool LINEAR>
 __global__ void __launch_bounds__(256) k_tuple_round(const u32 *__restrict__ nxt_in, u32 *__restrict__ nxt_out,
                                                      u8 *__restrict__ dr, const u32 *__restrict__ rank,
@@ -697,27 +747,41 @@ __global__ void __launch_bounds__(256) k_tuple_round(const u32 *__restrict__ nxt
     __shared__ u32 s_cnt[3];
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const u32 stride = gridDim.x * blockDim.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x * 4;
     u32 remain = 0, split = 0, seen = 0;
-    for (u64 i64 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i64 < n; i64 += stride) {
-        const u32 i = (u32)i64;
-        u32 m = ldg_stream_u32(nxt_in + i);
-        if (m == NONE32) continue;
-        seen++;
-        const u32 ki = finalize ? i : tuple_key2<LINEAR>(rank, FS, cidx, n, k, i);
-        u32 less = 0, eqn = NONE32, diff = 0;
-        for (int step = 0; m != i && step < TUPLE_MAX_STEPS; step++) {
-            const u32 km = finalize ? m : tuple_key2<LINEAR>(rank, FS, cidx, n, k, m);
-            less += km < ki;
-            diff |= km != ki;
-            if (km == ki && eqn == NONE32) eqn = m;
-            m = __ldg(nxt_in + m);
+    for (u64 i64 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; i64 < n; i64 += stride) {
+        const u32 i0 = (u32)i64;
+        u32 m[4];
+        if (i64 + 4 <= n) {
+            const uint4 v = ldg_stream_u4((const uint4 *)(nxt_in + i0));
+            m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) m[q] = (i64 + q < n) ? nxt_in[i0 + q] : NONE32;
         }
-        if (finalize) eqn = NONE32;
-        nxt_out[i] = eqn;
-        dr[i] = (u8)less;
-        remain += eqn != NONE32;
-        split += diff;
+        if ((m[0] & m[1] & m[2] & m[3]) == NONE32) continue;
+        u32 ki[4], km[4], mn[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            ki[q] = km[q] = 0; mn[q] = NONE32;
+            if (m[q] != NONE32) {
+                ki[q] = finalize ? i0 + q : tuple_key2<LINEAR>(rank, FS, cidx, n, k, i0 + q);
+                km[q] = finalize ? m[q] : tuple_key2<LINEAR>(rank, FS, cidx, n, k, m[q]);
+                mn[q] = __ldg(nxt_in + m[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (m[q] == NONE32) continue;
+            u32 less, eqn, diff;
+            tuple_walk<LINEAR>(nxt_in, rank, FS, cidx, n, k, finalize, i0 + q, ki[q], m[q], km[q], mn[q], less, eqn, diff);
+            if (finalize) eqn = NONE32;
+            nxt_out[i0 + q] = eqn;
+            dr[i0 + q] = (u8)less;
+            seen++;
+            remain += eqn != NONE32;
+            split += diff;
+        }
     }
     remain = warp_sum(remain); split = warp_sum(split); seen = warp_sum(seen);
     if (lane_id() == 0) {
@@ -732,13 +796,35 @@ __global__ void __launch_bounds__(256) k_tuple_round(const u32 *__restrict__ nxt
 __global__ void __launch_bounds__(256) k_tuple_apply(u32 *__restrict__ nxt_old, const u32 *__restrict__ nxt_new,
                                                      const u8 *__restrict__ dr, u32 *__restrict__ rank, u32 n)
 {
-    const u32 stride = gridDim.x * blockDim.x;
-    for (u64 i64 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i64 < n; i64 += stride) {
-        const u32 i = (u32)i64;
-        if (nxt_old[i] == NONE32) continue;
-        const u32 d = dr[i];
-        if (d) rank[i] += d;
-        if (nxt_new[i] == NONE32) nxt_old[i] = NONE32;
+    const u64 stride = (u64)gridDim.x * blockDim.x * 4;
+    for (u64 i64 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; i64 < n; i64 += stride) {
+        const u32 i0 = (u32)i64;
+        if (i64 + 4 <= n) {
+            uint4 o = *(const uint4 *)(nxt_old + i0);
+            if ((o.x & o.y & o.z & o.w) == NONE32) continue;
+            const uint4 nw = ldg_stream_u4((const uint4 *)(nxt_new + i0));
+            const u32 d4 = *(const u32 *)(dr + i0);
+            uint4 r = *(const uint4 *)(rank + i0);
+            const u32 l0 = o.x != NONE32, l1 = o.y != NONE32, l2 = o.z != NONE32, l3 = o.w != NONE32;
+            r.x += l0 ? (d4 & 255u) : 0u;
+            r.y += l1 ? ((d4 >> 8) & 255u) : 0u;
+            r.z += l2 ? ((d4 >> 16) & 255u) : 0u;
+            r.w += l3 ? (d4 >> 24) : 0u;
+            *(uint4 *)(rank + i0) = r;
+            // a position that became unique leaves the set in both buffers
+            if (l0 && nw.x == NONE32) o.x = NONE32;
+            if (l1 && nw.y == NONE32) o.y = NONE32;
+            if (l2 && nw.z == NONE32) o.z = NONE32;
+            if (l3 && nw.w == NONE32) o.w = NONE32;
+            *(uint4 *)(nxt_old + i0) = o;
+        } else {
+            for (u32 i = i0; i < n; i++) {
+                if (nxt_old[i] == NONE32) continue;
+                const u32 d = dr[i];
+                if (d) rank[i] += d;
+                if (nxt_new[i] == NONE32) nxt_old[i] = NONE32;
+            }
+        }
     }
 }
 

@@ -169,10 +169,15 @@ __global__ void __launch_bounds__(INV_NT) k_inv_lf_rank(const u8 *__restrict__ B
 }
 
 // ---- splitters ------------------------------------------------------------------------------------
-static __device__ __forceinline__ bool is_splitter(u32 i, u32 shift) { return ((i * 0x9E3779B1u) >> shift) == 0; }
+// Splitters are picked by a multiplicative hash of the index: density 2^-(32 - shift).  The
+// multiplier is a parameter: when the self-walk fallback runs over its work budget (a long cycle
+// that the hash happens to miss -- it is public and fixed, so an input can be built against it),
+// the host starts the inverse again with another multiplier and a denser set.
+struct SplHash { u32 mul, shift; };
+static __device__ __forceinline__ bool is_splitter(u32 i, SplHash h) { return ((i * h.mul) >> h.shift) == 0; }
 
 #define SP_TILE 4096
-__global__ void __launch_bounds__(256) k_inv_spl_count(u32 n, u32 shift, u32 *__restrict__ tilecnt)
+__global__ void __launch_bounds__(256) k_inv_spl_count(u32 n, SplHash shift, u32 *__restrict__ tilecnt)
 {
     __shared__ u32 ws[8];
     const u32 base = blockIdx.x * SP_TILE + threadIdx.x * 16;
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(256) k_inv_spl_count(u32 n, u32 shift, u32 *__
 // sid (two-walk path): sparse map element -> sublist id, written at splitter slots only.
 // blkoff (staged path): blkoff[b] = number of splitters below element 64 b; the id of the sublist
 // that starts at splitter p is blkoff[p >> 6] + the splitters in [p & ~63, p) (sid_of).
-__global__ void __launch_bounds__(256) k_inv_spl_write(u32 n, u32 shift, const u32 *__restrict__ tileoff,
+__global__ void __launch_bounds__(256) k_inv_spl_write(u32 n, SplHash shift, const u32 *__restrict__ tileoff,
                                                        u32 *__restrict__ spl, u32 *__restrict__ sid,
                                                        u32 *__restrict__ blkoff)
 {
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(256) k_inv_spl_write(u32 n, u32 shift, const u
             s++;
         }
 }
-static __device__ __forceinline__ u32 sid_of(const u32 *__restrict__ blkoff, u32 p, u32 shift)
+static __device__ __forceinline__ u32 sid_of(const u32 *__restrict__ blkoff, u32 p, SplHash shift)
 {
     u32 s = __ldg(blkoff + (p >> 6));
     for (u32 q = p & ~63u; q < p; q++) s += is_splitter(q, shift);
@@ -226,7 +231,7 @@ static __device__ __forceinline__ u32 sid_of(const u32 *__restrict__ blkoff, u32
 // access rate, not warp divergence.)
 // jm[s] = next sublist << 32 | smallest index; wlen[s] = sublist length; minfo[s] = (smallest
 // index, its offset).  visited (optional) gets one bit per element reached.  *total += lengths.
-__global__ void __launch_bounds__(128) k_inv_walk(const u32 *__restrict__ prev, u32 shift,
+__global__ void __launch_bounds__(128) k_inv_walk(const u32 *__restrict__ prev, SplHash shift,
                                                   const u32 *__restrict__ spl, u32 ns, const u32 *__restrict__ sid,
                                                   u64 *__restrict__ jm, u32 *__restrict__ wlen,
                                                   uint2 *__restrict__ minfo, u32 *__restrict__ visited,
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(128) k_inv_walk(const u32 *__restrict__ prev, 
 
 // second walk: srec[s] = (d of the splitter element, cycle length L, cycle offset off);
 // element at offset o of the sublist has d = (A + o) mod L and lands at out[n-1-off-d].
-__global__ void __launch_bounds__(128) k_inv_walk_place(const u32 *__restrict__ prev, u32 n, u32 shift,
+__global__ void __launch_bounds__(128) k_inv_walk_place(const u32 *__restrict__ prev, u32 n, SplHash shift,
                                                         const u32 *__restrict__ spl, u32 ns,
                                                         const uint4 *__restrict__ srec,
                                                         const u32 *__restrict__ Ctab, u8 *__restrict__ out)
@@ -341,14 +346,18 @@ __global__ void __launch_bounds__(256) k_inv_origin_publish(const u64 *__restric
 // fallback: elements no walk reached belong to cycles without a splitter: walk the whole cycle.
 // One thread per word of the visited bitmap.  urec[i] = (smallest index, d(i)), written (and
 // later read) only for unreached elements.
+// counters[0] += elements handled; counters[1] += steps (in units of 1024); *abort is raised once the
+// steps exceed budget_k x 1024: cycles of length L cost L steps per member here, L^2 per cycle.
 __global__ void __launch_bounds__(256) k_inv_self_walk(const u32 *__restrict__ prev, u32 n,
                                                        const u32 *__restrict__ visited, uint2 *__restrict__ urec,
-                                                       u32 *__restrict__ len_at_min, u32 *__restrict__ counters)
+                                                       u32 *__restrict__ len_at_min, u32 *__restrict__ counters,
+                                                       u32 budget_k, u32 *__restrict__ abort)
 {
     const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
     if ((u64)w * 32 >= n) return;
     u32 todo = ~visited[w];
     if ((u64)w * 32 + 32 > n) todo &= (1u << (n - w * 32)) - 1;
+    u32 spent = 0;
     while (todo) {
         const u32 i = w * 32 + (__ffs(todo) - 1);
         todo &= todo - 1;
@@ -357,12 +366,68 @@ __global__ void __launch_bounds__(256) k_inv_self_walk(const u32 *__restrict__ p
             if (j < mn) { mn = j; mstep = steps; }
             j = prev[j];
             steps++;
+            if ((++spent & 1023u) == 0) {
+                if (atomicAdd(counters + 1, 1u) >= budget_k) atomicExch(abort, 1u);
+                if (*(volatile u32 *)abort) return;
+            }
         }
         urec[i] = make_uint2(mn, (mstep == 0) ? 0 : steps - mstep);
         if (mn == i) len_at_min[i] = steps;
         atomicAdd(counters, 1u);
     }
 }
+
+// ---- finding the elements no walk reached, from the per-128 counts --------------------------------
+// deflist[0..*ndef) = blocks of 128 elements whose count is short (capacity cap; *ndef keeps counting)
+__global__ void __launch_bounds__(256) k_inv_find_deficient(const u32 *__restrict__ vcnt, u32 n, u32 *__restrict__ deflist,
+                                                            u32 cap, u32 *__restrict__ ndef)
+{
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;  // block of 128 elements
+    if ((u64)b * 128 >= n) return;
+    const u32 expect = min(128u, n - b * 128);
+    const u32 c = (vcnt[b >> 2] >> (8 * (b & 3))) & 255u;
+    if (c != expect) {
+        const u32 at = atomicAdd(ndef, 1u);
+        if (at < cap) deflist[at] = b;
+    }
+}
+// one thread per element of a deficient block: an element that some walk reached meets a splitter
+// when it follows prev (the end of its sublist); one that meets itself first lies on a cycle without
+// splitters and gets its bit in `visited` cleared (the bitmap starts all ones).  Same step budget.
+__global__ void __launch_bounds__(128) k_inv_verify_candidates(const u32 *__restrict__ prev, u32 n, SplHash h,
+                                                               const u32 *__restrict__ deflist, u32 ndef,
+                                                               u32 *__restrict__ visited, u32 *__restrict__ counters,
+                                                               u32 budget_k, u32 *__restrict__ abort)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((t >> 7) >= ndef) return;
+    const u32 i = deflist[t >> 7] * 128 + (t & 127);
+    if (i >= n) return;
+    u32 j = i, spent = 0;
+    for (;;) {
+        if (is_splitter(j, h)) return;  // reached
+        j = prev[j];
+        if (j == i) break;              // a cycle without splitters
+        if ((++spent & 1023u) == 0) {
+            if (atomicAdd(counters + 1, 1u) >= budget_k) atomicExch(abort, 1u);
+            if (*(volatile u32 *)abort) return;
+        }
+    }
+    atomicAnd(visited + (i >> 5), ~(1u << (i & 31)));
+}
+// many deficient blocks (inputs with very many short cycles): mark exactly, one bit per element
+__global__ void __launch_bounds__(128) k_inv_walk_mark(const u32 *__restrict__ prev, SplHash h,
+                                                       const u32 *__restrict__ spl, u32 ns, u32 *__restrict__ visited)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    u32 i = spl[s];
+    do {
+        atomicOr(visited + (i >> 5), 1u << (i & 31));
+        i = prev[i];
+    } while (!is_splitter(i, h));
+}
+
 __global__ void __launch_bounds__(256) k_inv_place_unreached(const u8 *__restrict__ B, u32 n,
                                                              const u32 *__restrict__ visited,
                                                              const uint2 *__restrict__ urec,
@@ -419,12 +484,13 @@ static __device__ __forceinline__ u32 byte_of_rank(const u32 *sC, u32 p)
     return c;
 }
 
-__global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ prev, u32 shift,
+__global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ prev, SplHash shift,
                                                         const u32 *__restrict__ spl, u32 ns, u32 Q,
                                                         const u32 *__restrict__ Ctab, u32 *__restrict__ nxt,
                                                         u32 *__restrict__ wlen, uint2 *__restrict__ minfo,
                                                         u8 *__restrict__ stage, u32 slot, u32 *__restrict__ cont,
-                                                        u32 *__restrict__ visited, u32 *__restrict__ total)
+                                                        u32 *__restrict__ visited, u32 *__restrict__ vcnt,
+                                                        u32 *__restrict__ total)
 {
     __shared__ u32 sC[257];
     for (u32 t = threadIdx.x; t < 257; t += blockDim.x) sC[t] = Ctab[t];
@@ -453,7 +519,11 @@ __global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ 
         }
         if (s != NONE32) {
             const u32 p = ldg_stream_u32(prev + i);
-            if (visited) atomicOr(visited + (i >> 5), 1u << (i & 31));
+            // who was reached?  Either one bit per element (n / 8 bytes: beyond ~512 MiB of input the
+            // bitmap falls out of L2 and every mark becomes a DRAM read-modify-write) or one 8-bit
+            // count per 128 elements (n / 128 bytes, L2-resident at every size; k_inv_find_deficient)
+            if (vcnt) atomicAdd(vcnt + (i >> 9), 1u << (8 * ((i >> 7) & 3)));
+            else if (visited) atomicOr(visited + (i >> 5), 1u << (i & 31));
             if (o < slot) {
                 const u32 c = byte_of_rank(sC, p);
                 const u32 b = o & 31, q = b >> 3;
@@ -495,7 +565,7 @@ __global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ 
 
 // jm[s] = id of the next sublist << 32 | smallest index of sublist s
 __global__ void __launch_bounds__(256) k_inv_resolve_next(const u32 *__restrict__ nxt, const uint2 *__restrict__ minfo,
-                                                          const u32 *__restrict__ blkoff, u32 shift, u32 ns,
+                                                          const u32 *__restrict__ blkoff, SplHash shift, u32 ns,
                                                           u64 *__restrict__ jm)
 {
     const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,7 +592,7 @@ __global__ void __launch_bounds__(256) k_inv_place_copy(const u8 *__restrict__ s
 }
 
 // the elements beyond offset slot of their sublist: a second walk from cont[s]
-__global__ void __launch_bounds__(128) k_inv_walk_tail(const u32 *__restrict__ prev, u32 n, u32 shift,
+__global__ void __launch_bounds__(128) k_inv_walk_tail(const u32 *__restrict__ prev, u32 n, SplHash shift,
                                                        const u32 *__restrict__ wlen, const u32 *__restrict__ cont,
                                                        u32 ns, u32 slot, const uint4 *__restrict__ srec,
                                                        const u32 *__restrict__ Ctab, u8 *__restrict__ out)

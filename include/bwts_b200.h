@@ -124,6 +124,7 @@ typedef struct {
     long   first_live;          /* forward: rotations still tied after the initial sort      */
     int    tuple_rounds;        /* forward: rounds in which the text-ordered tuple set ran   */
     long   tuple_live_sum;      /* forward: sum over those rounds of its members             */
+    int    inverse_attempts;    /* inverse: 1 + restarts with another splitter hash (fallback over budget) */
 } bwts_b200_stats;
 
 int bwts_b200_get_stats(const bwts_b200_ctx *ctx, bwts_b200_stats *out);
@@ -149,7 +150,9 @@ const char *bwts_b200_version(void);
  * binned from 512 Mi bytes), 10 = cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured: no
  * effect), 12 = inverse through two read-only walks (1) instead of the staged single walk, 13 =
  * sublists per warp of the staged walk, 14 = largest group the text-ordered tuple set takes (1 =
- * set switched off, 2..32; default 8).  value 0 = default.                               */
+ * set switched off, 2..32; default 8), 15 = inverse marks reached elements with one bit each (1)
+ * instead of one count per 128, 16 = step budget of the inverse's fallback walks per attempt
+ * (default 32 n).  value 0 = default.                                                    */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

@@ -390,6 +390,52 @@ def test_device_api_accepts_unaligned_input(bwts, ctx, oracle, gen):
         assert bytes(o.cpu().numpy()) == want_i, off
 
 
+def test_inverse_mark_modes_and_many_short_cycles(bwts, ctx, oracle, gen):
+    """the staged walk marks reached elements with one count per 128 (default) or one bit each (tune 15 = 1);
+    unreached elements are found from the short counts (few deficient blocks: candidates are tested one by
+    one) or, when very many blocks are short (a^n: every element is its own cycle), by an exact marking walk"""
+    rng = np.random.default_rng(13)
+    cases = [b"a" * 100_000, b"ab" * 60_000, bytes(rng.integers(0, 2, size=200_000, dtype=np.uint8)),
+             gen.make("text", 91, 1_000_000), gen.make("dna", 92, 1_500_000), helpers.fibonacci_word(120_000),
+             bytes(np.repeat(rng.integers(0, 256, size=3000, dtype=np.uint8), 40))]
+    try:
+        for x in cases:
+            want = oracle.inverse(x)
+            for mark in (0, 1):
+                bwts.tune(15, mark)
+                for shift in (0, 22, 29):
+                    bwts.tune(1, shift)
+                    assert ctx.inverse_host(x) == want, (len(x), mark, shift)
+    finally:
+        bwts.tune(15, 0)
+        bwts.tune(1, 0)
+
+
+def test_inverse_fallback_budget_restarts_with_another_hash(bwts, ctx, oracle):
+    """a cycle without splitters is walked by each of its members (L^2 steps): the fallback has a step budget,
+    and when it runs out the inverse starts again with another hash multiplier and denser splitters.
+    Input: 200 Lyndon factors of 8192 bytes each (first letter strictly smallest, decreasing from word to
+    word); with splitter density 2^-12 about 13 % of the 8192-cycles hold no splitter."""
+    rng = np.random.default_rng(5)
+    L = 8192
+    x = b"".join(bytes([c]) + bytes(rng.integers(c + 1, 256, size=L - 1, dtype=np.uint8)) for c in range(200, 0, -1))
+    y = ctx.forward_host(x)
+    assert y == oracle.forward(x) and ctx.stats()["factors"] == 200
+    try:
+        bwts.tune(1, 20)
+        bwts.tune(16, 1 << 20)
+        back = ctx.inverse_host(y)
+        st = ctx.stats()
+        assert back == x
+        assert st["inverse_attempts"] >= 2 and st["factors"] == 200
+        bwts.tune(16, 0)      # the default budget (32 n steps) lets the same input through without a restart
+        bwts.tune(1, 24)
+        assert ctx.inverse_host(y) == x and ctx.stats()["inverse_attempts"] == 1
+    finally:
+        bwts.tune(1, 0)
+        bwts.tune(16, 0)
+
+
 def test_suffix_array_seam(bwts, oracle, gen):
     for x in (b"banana", b"mississippi", b"a" * 1000, gen.make("text", 5, 200_000), gen.make("dna", 6, 300_000),
               helpers.fibonacci_word(50_000)):
@@ -445,7 +491,7 @@ def test_timings_use_the_reference_phase_labels(gen, tmp_path):
     diag = [ln for ln in p.stderr.splitlines() if ln.startswith("Factors:")]
     assert len(diag) == 1
     m = re.match(r"Factors:\s+(\d+); longest:\s+(\d+); alphabet bits: (\d+); initial depth: (\d+); "
-                 r"live after initial sort:\s+(\d+); doubling rounds: (\d+) \(warp-local (\d+), CTA-local (\d+)\); "
+                 r"live after initial sort:\s+(\d+); doubling rounds: (\d+) \(warp-local (\d+), CTA-local (\d+), tuple set (\d+)\); "
                  r"radix passes: (\d+); live sum: (\d+); workspace bytes/byte: ([0-9.]+)$", diag[0])
     assert m, diag[0]
     factors, longest, bits, depth, live0, rounds = (int(m.group(i)) for i in range(1, 7))
