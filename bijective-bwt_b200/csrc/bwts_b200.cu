@@ -120,6 +120,16 @@ static cudaEvent_t ctx_event(bwts_b200_ctx *ctx)
     return ctx->pool[ctx->pool_used++];
 }
 
+// BWTS_B200_SYNC=1 (debugging): wait for every kernel and name the one that failed
+static cudaError_t launch_check(const char *name, cudaStream_t st)
+{
+    static const bool sync = getenv("BWTS_B200_SYNC") != nullptr;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess && sync) fprintf(stderr, "[bwts_b200] kernel %s failed: %s\n", name, cudaGetErrorString(e));
+    return e;
+}
+
 // LAUNCH(class, algorithmic bytes, kernel, grid, block, args...)
 #define LAUNCH(KCLS_, NBYTES_, kern, grid, block, ...)                               \
     do {                                                                             \
@@ -129,7 +139,7 @@ static cudaEvent_t ctx_event(bwts_b200_ctx *ctx)
         kern<<<(grid), (block), 0, st>>>(__VA_ARGS__);                               \
         if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
         r__.phase = ctx->phase; ctx->recs.push_back(r__);                                                    \
-        CK(cudaGetLastError());                                                      \
+        CK(launch_check(#kern, st));                                                 \
     } while (0)
 
 static void stats_begin(bwts_b200_ctx *ctx, long len, int direction, cudaStream_t st)
@@ -176,8 +186,8 @@ static int arena_reserve(bwts_b200_ctx *ctx, size_t bytes)
     if (bytes <= ctx->arena_bytes) return 0;
     if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
     CK(cudaMalloc((void **)&ctx->arena, bytes));
-    CK(cudaMemset(ctx->arena, 0, bytes));
-    CK(cudaDeviceSynchronize());  // the legacy-stream memset does not order against non-blocking streams
+    // no clearing: every array is written (or memset on the transform's stream) before it is read; the one
+    // consumer of stale bytes, the look-back status region, is cleared per transform
     ctx->arena_bytes = bytes;
     return 0;
 }
@@ -423,6 +433,18 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     if (rc) return rc;
 
     CK(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
+    if (!t_decided && n >= (1u << 20)) {
+        // vote on the tuple set before the first re-rank: 64 Ki sorted neighbours; if most of the tied ones
+        // still agree 32 bytes further on, the ties come from long repeats (see k_sample_lcp).  Where the
+        // vote says no, the first small-group round gets a second look (survival of its ties, below).
+        const u32 samples = 1u << 16;
+        CK(cudaMemsetAsync(tcnt + 4, 0, 8, st));
+        LAUNCH(KC_TUPLE, 24.0 * samples, k_sample_lcp, samples / 256, 256, sb.k[sb.cur], sb.v[sb.cur], dT, n, samples, k0, 32u,
+               tcnt + 4);
+        rc = readback(ctx, st, tcnt + 4, 8);
+        if (rc) return rc;
+        if (ctx->h_small[0] >= samples / 16 && 2 * ctx->h_small[1] >= ctx->h_small[0]) { t_on = true; t_decided = true; }
+    }
     if (t_on) {  // every position starts outside the tuple set, in both buffers
         CK(cudaMemsetAsync(nxtT[0], 0xff, (size_t)n * 4, st));
         CK(cudaMemsetAsync(nxtT[1], 0xff, (size_t)n * 4, st));
@@ -838,6 +860,10 @@ static int inverse_attempt(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, c
         if (!urec) return BWTS_B200_EINTERNAL;
         LAUNCH(KC_INV_WALK, 12.0 * (n - reached), k_inv_self_walk, cdiv(nwords, 256), 256, prev, n, visited, urec,
                len_at_min, small + 4, bk, small + 12);
+        // out of budget: the records of the unreached elements are incomplete, nothing below may read them
+        rc = readback(ctx, st, small + 12, 4);
+        if (rc) return rc;
+        if (ctx->h_small[0]) { *over = true; return 0; }
         ctx->phase = 3;
     }
 
@@ -861,7 +887,6 @@ static int inverse_attempt(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, c
 
     rc = readback(ctx, st, small, 56);
     if (rc) return rc;
-    if (ctx->h_small[12]) { *over = true; return 0; }      // the fallback ran out of budget: the caller tries another hash
     if (g_tune_nomark) return 0;                            // timing experiment, the output is not checked
     if (ctx->h_small[8] != n) return BWTS_B200_EINTERNAL;  // cycle lengths must add up to n
     ctx->stats.splitters = ns;
@@ -1025,6 +1050,13 @@ extern "C" int bwts_b200_inverse_device(bwts_b200_ctx *ctx, const void *d_in, lo
 static std::mutex g_dev_mutex[MAX_DEV];
 static bwts_b200_ctx *g_dev_ctx[MAX_DEV];
 
+// host <-> device copies of the host-buffer entry points: pinned buffers go as one async copy,
+// pageable ones (the tools' mmap'ed input, map_file.c, and malloc'ed output) through the context's
+// ring of pinned chunks -- the memcpy into chunk c+1 runs while chunk c is on the bus, where a
+// pageable cudaMemcpy stages serially inside the driver.  Defined behind PinnedRing.
+static int stage_h2d(bwts_b200_ctx *ctx, u8 *d_dst, const u8 *src, size_t len, cudaStream_t st);
+static int stage_d2h(bwts_b200_ctx *ctx, u8 *dst, const u8 *d_src, size_t len, cudaStream_t st);
+
 static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, long len, unsigned char *out)
 {
     if (!ctx) return BWTS_B200_EINVAL;
@@ -1040,7 +1072,8 @@ static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, 
     cudaStream_t st = ctx->own_stream;
     apply_device_limits();
     CK(cudaEventRecord(ctx->ev_io0, st));
-    CK(cudaMemcpyAsync(d_in, in, (size_t)len, cudaMemcpyHostToDevice, st));
+    rc = stage_h2d(ctx, d_in, in, (size_t)len, st);
+    if (rc) return rc;
     ctx->io_in = d_in;  // tells the cores to skip the I/O region of the arena
     stats_begin(ctx, len, direction, st);
     rc = direction == 0 ? forward_core(ctx, d_in, (u32)len, d_out, nullptr, FWD_BWTS, st)
@@ -1048,7 +1081,8 @@ static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, 
     ctx->io_in = nullptr;
     if (rc) { cudaStreamSynchronize(st); cudaGetLastError(); return rc; }
     stats_end(ctx, st);
-    CK(cudaMemcpyAsync(out, d_out, (size_t)len, cudaMemcpyDeviceToHost, st));
+    rc = stage_d2h(ctx, out, d_out, (size_t)len, st);
+    if (rc) return rc;
     CK(cudaEventRecord(ctx->ev_io1, st));
     CK(cudaStreamSynchronize(st));
     float t = 0;
@@ -1193,6 +1227,46 @@ static int pipe_d2h(PinnedRing &ring, bool pinned, u8 *dst, const u8 *d_src, siz
         }
     }
     return 0;
+}
+
+static int stage_h2d(bwts_b200_ctx *ctx, u8 *d_dst, const u8 *src, size_t len, cudaStream_t st)
+{
+    bool pinned = len < 2 * PIPE_CHUNK || host_ptr_is_pinned(src);
+    if (!pinned && !ctx->pipe_ring_in) {
+        ctx->pipe_ring_in = new PinnedRing();
+        if (ctx->pipe_ring_in->init() != 0) {  // no pinned memory to be had: the plain copy still works
+            ctx->pipe_ring_in->destroy(); delete ctx->pipe_ring_in; ctx->pipe_ring_in = nullptr;
+            cudaGetLastError();
+            pinned = true;
+        }
+    }
+    if (pinned) {
+        CK(cudaMemcpyAsync(d_dst, src, len, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    size_t seq = 0;
+    const int rc = pipe_h2d(*ctx->pipe_ring_in, false, d_dst, src, len, st, seq);
+    if (rc) ctx->last_cuda = (int)cudaGetLastError();
+    return rc;
+}
+static int stage_d2h(bwts_b200_ctx *ctx, u8 *dst, const u8 *d_src, size_t len, cudaStream_t st)
+{
+    bool pinned = len < 2 * PIPE_CHUNK || host_ptr_is_pinned(dst);
+    if (!pinned && !ctx->pipe_ring_out) {
+        ctx->pipe_ring_out = new PinnedRing();
+        if (ctx->pipe_ring_out->init() != 0) {
+            ctx->pipe_ring_out->destroy(); delete ctx->pipe_ring_out; ctx->pipe_ring_out = nullptr;
+            cudaGetLastError();
+            pinned = true;
+        }
+    }
+    if (pinned) {
+        CK(cudaMemcpyAsync(dst, d_src, len, cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+    const int rc = pipe_d2h(*ctx->pipe_ring_out, false, dst, d_src, len, st);
+    if (rc) ctx->last_cuda = (int)cudaGetLastError();
+    return rc;
 }
 
 static long g_tune_pipeline = 0;  // 1 = no overlap between blocks on one device

@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *idx, const u
         if (s < cnt) maxlen = max(maxlen, ge[h] - gs[h]);
     }
     maxlen = warp_max(maxlen);
-    u32 pos[2] = {0, 0}, tied[2] = {0, 0};
+    u32 pos[2] = {0, 0};
     for (u32 o = 0; o < maxlen; o++) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -651,10 +651,20 @@ __global__ void __launch_bounds__(256) k_local_sort_warp(const u32 *idx, const u
             const u32 other = (t & 32) ? b : a;
             const u32 me = lane + 32 * h;
             pos[h] += (t < ge[h]) && ((other < r[h]) || (other == r[h] && t < me));
-            tied[h] |= (t < ge[h]) && (other == r[h]) && (t != me);
         }
     }
-    if (sample) {
+    if (sample) {  // block-uniform; the sampled blocks run the member loop a second time for the tie count
+        u32 tied[2] = {0, 0};
+        for (u32 o = 0; o < maxlen; o++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const u32 t = gs[h] + o;
+                const u32 a = __shfl_sync(FULL_MASK, r[0], t & 31);
+                const u32 b = __shfl_sync(FULL_MASK, r[1], t & 31);
+                const u32 other = (t & 32) ? b : a;
+                tied[h] |= (t < ge[h]) && (other == r[h]) && (t != lane + 32 * h);
+            }
+        }
         const u32 c = warp_sum((u32)(lane < cnt) + (u32)(lane + 32 < cnt));
         const u32 t = warp_sum(((lane < cnt) ? tied[0] : 0u) + ((lane + 32 < cnt) ? tied[1] : 0u));
         if (lane == 0) { atomicAdd(&s_surv[0], c); atomicAdd(&s_surv[1], t); }
@@ -709,6 +719,36 @@ static __device__ __forceinline__ u32 tuple_key2(const u32 *__restrict__ rank, c
         if (o >= len) o -= len;
     }
     return __ldg(rank + s + o);
+}
+
+// Is the tuple set worth switching on?  Sample of the freshly sorted initial keys: among the sampled
+// neighbours that tie on their k0 symbols, how many still agree on the `extra` bytes that follow?
+// Long repeats (copied DNA segments) answer "nearly all", text answers "hardly any".  Factor
+// boundaries are ignored (the cyclic wrap inside short factors cannot matter for a vote).
+// counters[0] += tied pairs sampled, counters[1] += those that agree further.
+__global__ void __launch_bounds__(256) k_sample_lcp(const u64 *__restrict__ keys, const u32 *__restrict__ idx,
+                                                    const u8 *__restrict__ T, u32 n, u32 samples, u32 k0, u32 extra,
+                                                    u32 *__restrict__ counters)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 tied = 0, deep = 0;
+    if (t < samples) {
+        const u32 j = (u32)(((u64)t * (n - 1)) / samples);  // < n - 1
+        if (keys[j] == keys[j + 1]) {
+            tied = 1;
+            const u64 a = (u64)idx[j] + k0, b = (u64)idx[j + 1] + k0;
+            if (a + extra <= n && b + extra <= n) {
+                deep = 1;
+                for (u32 e = 0; e < extra; e++)
+                    if (T[a + e] != T[b + e]) { deep = 0; break; }
+            }
+        }
+    }
+    tied = warp_sum(tied); deep = warp_sum(deep);
+    if (lane_id() == 0) {
+        if (tied) atomicAdd(counters, tied);
+        if (deep) atomicAdd(counters + 1, deep);
+    }
 }
 
 // One ring member's share of phase A: walks the ring from m (the member after i), key2 of i given.

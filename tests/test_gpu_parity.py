@@ -436,6 +436,35 @@ def test_inverse_fallback_budget_restarts_with_another_hash(bwts, ctx, oracle):
         bwts.tune(16, 0)
 
 
+def test_two_contexts_share_one_gpu_concurrently(bwts, oracle, gen):
+    """the C ABI allows one context per host thread on the same device: two threads, each with its own context
+    and stream, run transforms at the same time -- forward against inverse, then forward against forward (two
+    sets of look-back chains in flight, which only assume that each kernel's own CTAs start in index order)"""
+    import threading
+    xs = [gen.make("text", 61, 3_000_000), gen.make("dna", 62, 4_000_000)]
+    fw = [oracle.forward(x) for x in xs]
+    errors = []
+
+    def worker(which, direction, rounds):
+        try:
+            with bwts.Context(0) as c:
+                for _ in range(rounds):
+                    if direction == 0:
+                        assert c.forward_host(xs[which]) == fw[which], ("forward", which)
+                    else:
+                        assert c.inverse_host(fw[which]) == xs[which], ("inverse", which)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    for plan in (((0, 0, 6), (1, 1, 6)), ((0, 0, 5), (1, 0, 5)), ((0, 1, 5), (1, 1, 5))):
+        threads = [threading.Thread(target=worker, args=a) for a in plan]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+
+
 def test_suffix_array_seam(bwts, oracle, gen):
     for x in (b"banana", b"mississippi", b"a" * 1000, gen.make("text", 5, 200_000), gen.make("dna", 6, 300_000),
               helpers.fibonacci_word(50_000)):
