@@ -46,6 +46,8 @@ static long g_tune_emit = 0;       // emit: 0 = binned from 512 Mi bytes, 1 = al
 static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L set
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
+static long g_tune_ctasort = 0;    // CTA-local sort: 0 = radix in shared memory, 1 = bitonic network (round 1)
+static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = hierarchical with CTA-wide comparisons, 1 = Hillis-Steele levels
 static long g_tune_tmax = 0;       // tuple set: largest group it takes (0 = 8, 1 = set switched off, 2..32)
 static long g_tune_invpath = 0;    // inverse: 0 = staged single walk (default), 1 = two read-only walks (round 1)
 static long g_tune_invq = 0;       // inverse staged walk: sublists per warp (0 = auto: one full wave of warps)
@@ -364,7 +366,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         const u32 nch = cdiv(n, chunk), ngroups = cdiv(nch, LY_GROUP);
         u32 *chunk_last = arena_take<u32>(ctx, nch);
         u32 *group_min = arena_take<u32>(ctx, ngroups);
-        u32 *group_alt = arena_take<u32>(ctx, ngroups);
+        u32 *group_alt = arena_take<u32>(ctx, (size_t)ngroups + ngroups / 8 + 512);
         if (!chunk_last || !group_min || !group_alt) return BWTS_B200_EINTERNAL;
         CK(cudaMemsetAsync(flags, 0, n, st));
         // work budgets: all Duval threads together may run n bytes (at least 32 MiB) past their
@@ -378,14 +380,37 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         if (nch > 1) {
             LAUNCH(KC_LYNDON, 0, k_chunkmin_reduce, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk_last, nch,
                    group_min, ngroups, bud_warp);
-            u32 *gin = group_min, *gout = group_alt;
-            for (u32 stride = 1; stride < ngroups; stride <<= 1) {
-                LAUNCH(KC_LYNDON, 0, k_chunkmin_level, cdiv((u64)ngroups * 32, 128), 128, dT, n, gin, gout, ngroups,
-                       stride, bud_warp);
-                u32 *t = gin; gin = gout; gout = t;
+            if (g_tune_lyscan == 1) {
+                // Hillis-Steele levels over the groups (round 1): ngroups log ngroups warp-wide comparisons
+                u32 *gin = group_min, *gout = group_alt;
+                for (u32 stride = 1; stride < ngroups; stride <<= 1) {
+                    LAUNCH(KC_LYNDON, 0, k_chunkmin_level, cdiv((u64)ngroups * 32, 128), 128, dT, n, gin, gout, ngroups,
+                           stride, bud_warp);
+                    u32 *t = gin; gin = gout; gout = t;
+                }
+                LAUNCH(KC_LYNDON, 0, k_chunk_threshold, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk, nch, flags,
+                       chunk_last, gin, 0, ngroups, bud_warp);
+            } else {
+                // reduce 32 -> 1 until one CTA can scan the top, then hand the exclusive prefixes back down
+                LyBudget bud_cta = {small + 3, g_tune_lyndon ? 0u : (64u << 10), small + 4};  // KiB per CTA
+                u32 *val[8], *pre[8], cnt[8];
+                int top = 0;
+                val[0] = group_min; cnt[0] = ngroups;
+                u32 *pool = group_alt;  // ngroups + ngroups / 8 + 512 words: prefixes of level 0, then the upper levels
+                pre[0] = pool; pool += ngroups;
+                while (cnt[top] > LY_GROUP && top < 6) {
+                    cnt[top + 1] = cdiv(cnt[top], LY_GROUP);
+                    val[top + 1] = pool; pool += cnt[top + 1];
+                    pre[top + 1] = pool; pool += cnt[top + 1];
+                    LAUNCH(KC_LYNDON, 0, k_sufmin_reduce_cta, cnt[top + 1], LY_CTA, dT, n, val[top], cnt[top], val[top + 1], bud_cta);
+                    top++;
+                }
+                for (int l = top; l >= 0; l--)
+                    LAUNCH(KC_LYNDON, 0, k_sufmin_down_cta, cdiv(cnt[l], LY_GROUP), LY_CTA, dT, n, val[l], cnt[l],
+                           l == top ? (const u32 *)nullptr : pre[l + 1], pre[l], bud_cta);
+                LAUNCH(KC_LYNDON, 0, k_chunk_threshold, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk, nch, flags,
+                       chunk_last, pre[0], 1, ngroups, bud_warp);
             }
-            LAUNCH(KC_LYNDON, 0, k_chunk_threshold, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk, nch, flags,
-                   chunk_last, gin, ngroups, bud_warp);
         }
     }
     if (!linear) {
@@ -638,12 +663,22 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                     LaunchRec r__;
                     r__.cls = KC_LOCAL_SORT; r__.bytes = 32.0 * mL; r__.e0 = r__.e1 = nullptr; r__.name = "k_local_sort_cta";
                     if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
-                    if (!linear)
-                        k_local_sort_cta<false><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
-                            sb.v[sb.cur], gst, mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
-                    else
-                        k_local_sort_cta<true><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
-                            sb.v[sb.cur], gst, mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                    if (g_tune_ctasort == 1) {  // the bitonic network of round 1
+                        if (!linear)
+                            k_local_sort_cta<false><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
+                                sb.v[sb.cur], gst, mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                        else
+                            k_local_sort_cta<true><<<cdiv(mL, LS_T), LS_NT, LS_CAP * sizeof(u64), st>>>(
+                                sb.v[sb.cur], gst, mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                    } else {
+                        r__.name = "k_local_sort_cta_radix";
+                        if (!linear)
+                            k_local_sort_cta_radix<false><<<cdiv(mL, LS_T), LSR_NT, LsrSmem::bytes, st>>>(
+                                sb.v[sb.cur], gst, mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                        else
+                            k_local_sort_cta_radix<true><<<cdiv(mL, LS_T), LSR_NT, LsrSmem::bytes, st>>>(
+                                sb.v[sb.cur], gst, mL, rank, FS, cidx, (u32)k, kb, n, sb.k[sb.cur ^ 1], sb.v[sb.cur ^ 1]);
+                    }
                     if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
                     r__.phase = ctx->phase; ctx->recs.push_back(r__);
                     CK(cudaGetLastError());
@@ -957,6 +992,8 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     OS_ATTR(u64, 512, 8, 3, 8);
     OS_ATTR(u64, 256, 16, 3, 8);
     OS_ATTR(u32, 384, 12, 3, 4);
+    cudaFuncSetAttribute(k_local_sort_cta_radix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LsrSmem::bytes);
+    cudaFuncSetAttribute(k_local_sort_cta_radix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LsrSmem::bytes);
     cudaFuncSetAttribute(k_local_sort_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LS_CAP * sizeof(u64)));
     cudaFuncSetAttribute(k_local_sort_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LS_CAP * sizeof(u64)));
 #undef OS_ATTR
@@ -997,7 +1034,8 @@ extern "C" int bwts_b200_reserve(bwts_b200_ctx *ctx, long max_len)
     if (!ctx || max_len <= 0) return BWTS_B200_EINVAL;
     if (max_len > BWTS_B200_MAX_LEN) return BWTS_B200_ETOOBIG;
     CK(cudaSetDevice(ctx->device));
-    return arena_reserve(ctx, workspace_bytes((size_t)max_len));
+    // sized for the host-buffer calls too (their input and output live in front of the workspace)
+    return arena_reserve(ctx, workspace_bytes((size_t)max_len) + 2 * (size_t)max_len + 1024);
 }
 
 static int check_len(const void *in, long len, void *out)
@@ -1536,6 +1574,8 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 12) { g_tune_invpath = value; return 0; }
     if (key == 14) { if (value < 0 || value > 32) return BWTS_B200_EINVAL; g_tune_tmax = value; return 0; }
     if (key == 15) { g_tune_invmark = value; return 0; }
+    if (key == 17) { g_tune_lyscan = value; return 0; }
+    if (key == 18) { g_tune_ctasort = value; return 0; }
     if (key == 16) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invbudget = value; return 0; }
     if (key == 13) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invq = value; return 0; }
     return BWTS_B200_EINVAL;

@@ -985,6 +985,181 @@ __global__ void __launch_bounds__(LS_NT, 2) k_local_sort_cta(const u32 *__restri
     }
 }
 
+// ---- CTA-local sort, radix form ---------------------------------------------------------------------
+// Same ownership and gather as k_local_sort_cta; the bitonic network (91 stages over 8192 words,
+// ~24 warp instructions per slot, 15 ms per round of the tiled C3 text) gives way to a stable LSD
+// radix sort inside shared memory: ceil(kb / 8) passes over key2, then two over the local group start
+// when the CTA owns more than one group.  A pass = the onesweep kernel's ranking (digit byte,
+// ballot masks, per-warp counters) on elements held in registers, a scan of the 256 digit counts,
+// a scatter back into the same arrays.  Only (key2, source slot) move; the group start is looked up by
+// source slot.  73 KB of shared memory, two CTAs per SM.
+#define LSR_NT 512
+#define LSR_IPT 16  // LS_CAP / LSR_NT
+struct LsrSmem {
+    static constexpr size_t r = 0;                                   // u32[LS_CAP] key2, current order
+    static constexpr size_t s = r + sizeof(u32) * LS_CAP;            // u16[LS_CAP] source slot, current order
+    static constexpr size_t g = s + sizeof(u16) * LS_CAP;            // u16[LS_CAP] local group start BY SOURCE SLOT
+    static constexpr size_t wcnt = g + sizeof(u16) * LS_CAP;         // u16[16][256]
+    static constexpr size_t dstart = wcnt + sizeof(u16) * (LSR_NT / 32) * 256;  // u32[256]
+    static constexpr size_t wsum = dstart + sizeof(u32) * 256;       // u32[8]
+    static constexpr size_t bytes = wsum + 64;
+};
+
+template <bool LINEAR>
+__global__ void __launch_bounds__(LSR_NT, 2) k_local_sort_cta_radix(const u32 *__restrict__ idx, const u32 *__restrict__ gst,
+                                                                    u32 m, const u32 *__restrict__ rank,
+                                                                    const u32 *__restrict__ FS, const u32 *__restrict__ cidx,
+                                                                    u32 k, u32 kb, u32 n, u64 *__restrict__ keys_out,
+                                                                    u32 *__restrict__ idx_out)
+{
+    extern __shared__ __align__(16) u8 lsr_smem[];
+    u32 *s_r = (u32 *)(lsr_smem + LsrSmem::r);
+    u16 *s_s = (u16 *)(lsr_smem + LsrSmem::s);
+    u16 *s_g = (u16 *)(lsr_smem + LsrSmem::g);
+    u16(*s_wcnt)[256] = (u16(*)[256])(lsr_smem + LsrSmem::wcnt);
+    u32 *s_dstart = (u32 *)(lsr_smem + LsrSmem::dstart);
+    u32 *s_wsum = (u32 *)(lsr_smem + LsrSmem::wsum);
+    constexpr int NW = LSR_NT / 32;
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 c = blockIdx.x;
+    const u32 lo = __ldg(gst + c * LS_T);
+    const u32 hi = ((u64)(c + 1) * LS_T < m) ? __ldg(gst + (c + 1) * LS_T) : m;
+    const u32 cnt = hi - lo;
+    if (cnt == 0 || cnt > LS_CAP) return;  // nothing owned / refused by k_ls_probe beforehand
+    const u32 ipt = (cnt + LSR_NT - 1) / LSR_NT;  // 1 .. 16 elements per thread
+    const u32 P = ipt * LSR_NT;
+
+    // gather; pads carry the largest key2 and a group start no real group has (groups have >= 2 members)
+    bool multi = false;
+    for (u32 s = tid; s < P; s += LSR_NT) {
+        u32 r = 0xffffffffu, g = 0x1fffu;
+        if (s < cnt) {
+            const u32 j = lo + s;
+            const u32 i = ldg_stream_u32(idx + j);
+            g = ldg_stream_u32(gst + j) - lo;
+            if (LINEAR) {
+                const u64 t = (u64)i + k;
+                r = (t < n) ? __ldg(rank + (u32)t) + 1 : 0;
+            } else {
+                const u32 f = factor_of(FS, cidx, i);
+                const u32 fs = __ldg(FS + f), len = __ldg(FS + f + 1) - fs;
+                u32 o = i - fs;
+                if (len > 1) {
+                    o += (k < len) ? k : k % len;
+                    if (o >= len) o -= len;
+                }
+                r = __ldg(rank + fs + o);
+            }
+            multi |= g != 0;
+        }
+        s_r[s] = r;
+        s_s[s] = (u16)s;
+        s_g[s] = (u16)g;
+    }
+    __syncthreads();
+    // already in order?  (most groups of a repetitive input see one key2 for all members in most rounds)
+    bool unsorted = false;
+    for (u32 s = tid; s + 1 < cnt; s += LSR_NT)
+        unsorted |= (s_g[s] == s_g[s + 1]) && (s_r[s] > s_r[s + 1]);
+    const bool need_sort = __syncthreads_or(unsorted);
+    const bool many_groups = __syncthreads_or(multi);
+
+    const int rp = (int)((kb + 7) / 8), gp = many_groups ? 2 : 0;
+    const u32 lt = lanemask_lt();
+    const u32 wpos = warp * (32 * ipt) + lane;  // warp-major: the order of (warp, j, lane) is the order of positions
+    u16 *wc = s_wcnt[warp];
+    for (int pass = 0; need_sort && pass < rp + gp; pass++) {
+        for (u32 i = tid; i < NW * 256 / 2; i += LSR_NT) ((u32 *)s_wcnt)[i] = 0;
+        __syncthreads();  // counters zeroed; the previous pass's scatter is complete
+        u32 rr[LSR_IPT], dpk[LSR_IPT / 4];
+        u32 sspk[LSR_IPT / 2], rnkpk[LSR_IPT / 2];  // source slots and in-warp ranks, two 16-bit values per word
+#pragma unroll
+        for (int h0 = 0; h0 < LSR_IPT; h0 += 8) {  // eight elements at a time: their peer masks live in registers
+            u32 peers[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int j = h0 + jj;
+                if ((j & 3) == 0) dpk[j >> 2] = 0;
+                if ((j & 1) == 0) { sspk[j >> 1] = 0; rnkpk[j >> 1] = 0; }
+                peers[jj] = 0;
+                rr[j] = 0;
+                if ((u32)j < ipt) {
+                    const u32 p = wpos + j * 32;
+                    rr[j] = s_r[p];
+                    const u32 sj = s_s[p];
+                    sspk[j >> 1] |= sj << (16 * (j & 1));
+                    const u32 dj = (pass < rp) ? ((rr[j] >> (8 * pass)) & 255u)
+                                               : (((u32)s_g[sj] >> (8 * (pass - rp))) & 255u);
+                    dpk[j >> 2] |= dj << (8 * (j & 3));
+                    u32 pm = FULL_MASK;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const u32 bit = (dj >> b) & 1u;
+                        const u32 bal = __ballot_sync(FULL_MASK, bit);
+                        pm &= bal ^ (bit - 1u);
+                    }
+                    peers[jj] = pm;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int j = h0 + jj;
+                if ((u32)j < ipt) {
+                    const u32 dj = (dpk[j >> 2] >> (8 * (j & 3))) & 255u;
+                    const int leader = __ffs(peers[jj]) - 1;
+                    u32 before = 0;
+                    if ((int)lane == leader) {
+                        before = wc[dj];
+                        wc[dj] = (u16)(before + __popc(peers[jj]));
+                    }
+                    before = __shfl_sync(FULL_MASK, before, leader);
+                    rnkpk[j >> 1] |= ((before + __popc(peers[jj] & lt)) & 0xffffu) << (16 * (j & 1));
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();  // every element is in registers, every warp's counts are final
+        u32 blockcnt = 0, dsum = 0;
+        if (tid < 256) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const u32 cw = s_wcnt[w][tid];
+                s_wcnt[w][tid] = (u16)blockcnt;  // this warp's base inside the digit's run
+                blockcnt += cw;
+            }
+            const u32 incl = warp_incl_sum(blockcnt);
+            if (lane == 31) s_wsum[warp] = incl;
+            dsum = incl - blockcnt;
+        }
+        __syncthreads();
+        if (tid < 256) {
+#pragma unroll
+            for (int w = 0; w < 8; w++)
+                if (w < (int)warp) dsum += s_wsum[w];
+            s_dstart[tid] = dsum;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < LSR_IPT; j++) {
+            if ((u32)j < ipt) {
+                const u32 dj = (dpk[j >> 2] >> (8 * (j & 3))) & 255u;
+                const u32 dst = s_dstart[dj] + wc[dj] + ((rnkpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+                s_r[dst] = rr[j];
+                s_s[dst] = (u16)(sspk[j >> 1] >> (16 * (j & 1)));
+            }
+        }
+        __syncthreads();  // the scatter read the warp bases: nobody may zero the counters before everyone is through
+    }
+    __syncthreads();
+    for (u32 s = tid; s < cnt; s += LSR_NT) {
+        const u32 src = s_s[s];
+        const u32 g = s_g[src];
+        keys_out[lo + s] = ((u64)(lo + g) << kb) | (u64)s_r[s];
+        idx_out[lo + s] = __ldg(idx + lo + src);
+    }
+}
+
 // ---- emit -----------------------------------------------------------------------------------------
 // out[rank[i]] = T[i-1] for every position that does not start a factor and whose rank lies in
 // [lo, hi).  Large outputs are emitted in rank windows small enough to stay in L2, so the

@@ -158,6 +158,105 @@ __global__ void __launch_bounds__(128) k_chunkmin_level(const u8 *__restrict__ T
     if (lane_id() == 0) out[g] = v;
 }
 
+// ---- 2b. the same scan, work-efficient, with CTA-wide comparisons above the first level -------
+// The Hillis-Steele levels above compare ngroups * log2(ngroups) pairs of suffixes; on periodic
+// inputs (the 64 KiB-tiled C3 text: chunk minima of different tile copies agree for up to 1 MiB)
+// every comparison streams megabytes and the levels cost 30 ms of a 36 ms boundary search.  Here:
+// reduce 32 -> 1 level by level (k_sufmin_reduce_cta), then hand the exclusive prefixes back down
+// (k_sufmin_down_cta): ~2 * ngroups comparisons in all, each done by a whole CTA (32 KiB per step),
+// because the upper levels have few groups and a single warp would crawl through a 1 MiB match.
+#define LY_CTA 1024
+struct LyCtaShared {
+    u32 cand[2][LY_CTA / 32];
+    u32 res, stop;
+};
+// T[a..n) < T[b..n), a != b; all LY_CTA threads of the block call it with the same arguments.
+static __device__ bool suffix_less_cta(const u8 *__restrict__ T, u32 n, u32 a, u32 b, LyCtaShared &sh,
+                                       const LyBudget &bud, u32 &spent)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u64 off = 0;
+    for (u32 it = 0;; it++) {
+        const u64 pa = (u64)a + off + (u64)tid * 32, pb = (u64)b + off + (u64)tid * 32;
+        u32 first = 4;  // index of my first differing (or unsafe) 8-byte word
+        if (pa + 40 <= n && pb + 40 <= n) {
+            u64 x[4], y[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { x[q] = load8_unaligned(T + pa + 8 * q); y[q] = load8_unaligned(T + pb + 8 * q); }
+#pragma unroll
+            for (int q = 3; q >= 0; q--) if (x[q] != y[q]) first = q;
+        } else {
+            first = 0;  // too close to the end (or past it): the byte loop decides
+        }
+        const u32 mine = warp_min(first < 4 ? tid : NONE32);
+        u32 *cand = sh.cand[it & 1];
+        if (lane == 0) cand[warp] = mine;
+        if (tid == 0 && (it & 63) == 63) {
+            spent += 64 * (LY_CTA * 32 / 1024);  // KiB compared since the last check
+            if (spent > bud.limit) atomicExch(bud.abort, 1u);
+            sh.stop = *(volatile u32 *)bud.abort;
+        }
+        __syncthreads();
+        u32 best = (lane < LY_CTA / 32) ? cand[lane] : NONE32;
+        best = warp_min(best);
+        if (sh.stop) return false;  // over budget: the result is meaningless, the caller winds down
+        if (best == NONE32) { off += (u64)LY_CTA * 32; continue; }
+        if (tid == best) {
+            u64 p = pa + 8 * first, q = pb + 8 * first;
+            if (p > n) p = n;  // a window that starts past the end
+            if (q > n) q = n;
+            bool less;
+            for (;;) {
+                if (p >= n || q >= n) { less = p >= n; break; }  // the suffix that ends first is the smaller one
+                const u8 ca = T[p], cb = T[q];
+                if (ca != cb) { less = ca < cb; break; }
+                p++; q++;
+            }
+            sh.res = less ? 1u : 0u;
+        }
+        __syncthreads();
+        return sh.res != 0;
+    }
+}
+static __device__ __forceinline__ u32 suffix_min_cta(const u8 *T, u32 n, u32 a, u32 b, LyCtaShared &sh, const LyBudget &bud,
+                                                     u32 &spent)
+{
+    if (a == NONE32) return b;
+    if (b == NONE32) return a;
+    const bool less = suffix_less_cta(T, n, b, a, sh, bud, spent);
+    __syncthreads();  // sh.res / sh.cand are reused by the next comparison
+    return less ? b : a;
+}
+
+// out[g] = smallest suffix among in[32 g .. 32 g + 31]   (one CTA per g)
+__global__ void __launch_bounds__(LY_CTA) k_sufmin_reduce_cta(const u8 *__restrict__ T, u32 n, const u32 *__restrict__ in,
+                                                              u32 nin, u32 *__restrict__ out, LyBudget bud)
+{
+    __shared__ LyCtaShared sh;
+    if (threadIdx.x == 0) sh.stop = 0;
+    __syncthreads();
+    const u32 g = blockIdx.x, lo = g * LY_GROUP, hi = min(nin, lo + LY_GROUP);
+    u32 run = NONE32, spent = 0;
+    for (u32 t = lo; t < hi; t++) run = suffix_min_cta(T, n, run, in[t], sh, bud, spent);
+    if (threadIdx.x == 0) out[g] = run;
+}
+// excl[32 g + j] = smallest suffix among (everything before group g) and in[32 g .. 32 g + j - 1];
+// parent_excl == nullptr: nothing lies before group 0 (top level, one CTA)
+__global__ void __launch_bounds__(LY_CTA) k_sufmin_down_cta(const u8 *__restrict__ T, u32 n, const u32 *__restrict__ in,
+                                                            u32 nin, const u32 *__restrict__ parent_excl,
+                                                            u32 *__restrict__ excl, LyBudget bud)
+{
+    __shared__ LyCtaShared sh;
+    if (threadIdx.x == 0) sh.stop = 0;
+    __syncthreads();
+    const u32 g = blockIdx.x, lo = g * LY_GROUP, hi = min(nin, lo + LY_GROUP);
+    u32 run = parent_excl ? parent_excl[g] : NONE32, spent = 0;
+    for (u32 t = lo; t < hi; t++) {
+        if (threadIdx.x == 0) excl[t] = run;
+        if (t + 1 < hi) run = suffix_min_cta(T, n, run, in[t], sh, bud, spent);
+    }
+}
+
 // ---- 3. per chunk: drop the marks that are not below the minimum of everything before ----
 // position of the j-th (0-based) mark in [b,e); every lane owns a contiguous slice.
 static __device__ u32 select_mark_warp(const u8 *flags, u32 b, u32 e, u32 j)
@@ -185,13 +284,15 @@ static __device__ void clear_flags_warp(u8 *flags, u32 lo, u32 hi)
 
 __global__ void __launch_bounds__(128) k_chunk_threshold(const u8 *__restrict__ T, u32 n, u32 chunk, u32 nch,
                                                          u8 *__restrict__ flags, const u32 *__restrict__ chunk_last,
-                                                         const u32 *__restrict__ group_incl, u32 ngroups,
-                                                         LyBudget bud)
+                                                         const u32 *__restrict__ group_pre, int pre_is_exclusive,
+                                                         u32 ngroups, LyBudget bud)
 {
     const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= ngroups) return;
     const u32 lo = g * LY_GROUP, hi = min(nch, lo + LY_GROUP);
-    u32 run = g ? group_incl[g - 1] : NONE32;
+    // smallest suffix of everything before this group: exclusive prefixes (hierarchical scan) or the
+    // inclusive ones of the Hillis-Steele levels
+    u32 run = pre_is_exclusive ? group_pre[g] : (g ? group_pre[g - 1] : NONE32);
     u32 spent = 0;
     for (u32 t = lo; t < hi; t++) {
         const u32 mlast = chunk_last[t];

@@ -161,6 +161,44 @@ def test_full_size_properties_c3_c4(bwts, gen, kind, seed, n):
         del back, y
 
 
+def test_full_size_c6_above_2_30_through_the_tools(gen):
+    """the reference accepts any len < 2^31 (mk_bwts_sa.c:26-27, unbwts.c:12-13): a 1.5 GiB DNA file goes through
+    the drop-in tools, `bin/mk_bwts in out` then `bin/unbwts out back`; the forward file's SHA-256 equals
+    the unmodified reference's (tests/golden/fullsize.json, 748 s of one host core), the round trip is exact,
+    and the diagnostics line reports the workspace per input byte"""
+    import hashlib
+    import re
+    import shutil
+    import tempfile
+    if "C6" not in FULLSIZE:
+        pytest.skip("tests/golden/fullsize.json has no C6 entry")
+    gold = FULLSIZE["C6"]
+    bindir = helpers.PKG / "bin"
+    td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        src, mid, back = (os.path.join(td, f) for f in ("in", "mid", "back"))
+        x = gen.make(gold["kind"], gold["seed"], gold["n"])
+        assert helpers.sha256(x) == gold["input_sha256"]
+        with open(src, "wb") as f:
+            f.write(x)
+        env = dict(os.environ, BWTS_B200_TIMINGS="1")
+        p = subprocess.run([str(bindir / "mk_bwts"), src, mid], capture_output=True, text=True, env=env)
+        assert p.returncode == 0, p.stderr
+        m = re.search(r"workspace bytes/byte: ([0-9.]+)", p.stderr)
+        assert m and 60.0 <= float(m.group(1)) <= 75.0, p.stderr
+        h = hashlib.sha256()
+        with open(mid, "rb") as f:
+            for blk in iter(lambda: f.read(1 << 24), b""):
+                h.update(blk)
+        assert h.hexdigest() == gold["fwd_sha256"], "differs from the reference's mk_bwts output"
+        p = subprocess.run([str(bindir / "unbwts"), mid, back], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        with open(back, "rb") as f:
+            assert f.read() == x
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+
+
 def test_oracle_sample_16mib(ctx, oracle, gen):
     x = gen.make("text", 2, 16 << 20)
     assert ctx.forward_host(x) == oracle.forward(x)
@@ -272,14 +310,17 @@ def test_cta_local_sort_path_and_radix_path_agree(bwts, ctx, oracle, gen):
         for local_off in (0, 1):
             bwts.tune(3, local_off)
             bwts.tune(8, 0)
-            a = ctx.forward_host(x)
+            a = ctx.forward_host(x)          # CTA-local sort = radix in shared memory (default)
             used += ctx.stats()["cta_rounds"]
+            bwts.tune(18, 1)
+            a2 = ctx.forward_host(x)         # CTA-local sort = the bitonic network
+            bwts.tune(18, 0)
             bwts.tune(8, 1)
             b = ctx.forward_host(x)
             assert ctx.stats()["cta_rounds"] == 0
             bwts.tune(8, 0)
             bwts.tune(3, 0)
-            assert a == want and b == want
+            assert a == want and a2 == want and b == want
     assert used > 0, "the CTA-local sort never ran"
     # suffix-array mode (linear successor) through the same kernel
     y = gen.make("tiled", 83, 700_000)
@@ -614,6 +655,25 @@ def test_lyndon_suffix_sort_fallback(bwts, ctx, oracle, gen):
             assert ctx.forward_host(x) == oracle.forward(x), name
     finally:
         bwts.tune(4, 0)
+
+
+def test_lyndon_scan_variants_agree(bwts, ctx, oracle, gen):
+    """the chunk-minimum prefix scan: hierarchical with CTA-wide comparisons (default) and the Hillis-Steele
+    levels of round 1 (tune 17 = 1), on inputs with short and with very long common prefixes between chunk
+    minima (tiled text), with small chunks so that several levels exist"""
+    cases = [gen.make("tiled", 85, 3_000_000), gen.make("text", 86, 2_000_000), gen.make("dna", 87, 2_000_000),
+             helpers.fibonacci_word(300_000), helpers.families(200_000)["ww"], helpers.families(200_000)["descending"]]
+    try:
+        for x in cases:
+            want = oracle.forward(x)
+            for chunk in (0, 64, 16):
+                bwts.tune(0, chunk)
+                for scan in (0, 1):
+                    bwts.tune(17, scan)
+                    assert ctx.forward_host(x) == want, (len(x), chunk, scan)
+    finally:
+        bwts.tune(17, 0)
+        bwts.tune(0, 0)
 
 
 def test_periodic_inputs_trigger_the_fallback_by_budget(bwts, ctx, oracle):
