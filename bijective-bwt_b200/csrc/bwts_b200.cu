@@ -47,7 +47,7 @@ static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
 static long g_tune_ctasort = 0;    // CTA-local sort: 0 = radix in shared memory, 1 = bitonic network (round 1)
-static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = hierarchical with CTA-wide comparisons, 1 = Hillis-Steele levels
+static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = chosen by the first level's match lengths, 1 = Hillis-Steele levels, 2 = CTA-wide levels
 static long g_tune_tmax = 0;       // tuple set: largest group it takes (0 = 8, 1 = set switched off, 2..32)
 static long g_tune_invpath = 0;    // inverse: 0 = staged single walk (default), 1 = two read-only walks (round 1)
 static long g_tune_invq = 0;       // inverse staged walk: sublists per warp (0 = auto: one full wave of warps)
@@ -379,8 +379,17 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                bud_thread);
         if (nch > 1) {
             LAUNCH(KC_LYNDON, 0, k_chunkmin_reduce, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk_last, nch,
-                   group_min, ngroups, bud_warp);
-            if (g_tune_lyscan == 1) {
+                   group_min, ngroups, bud_warp, small + 6);
+            // which scan over the groups?  Where the first level's comparisons were short (text, DNA: a few bytes
+            // decide) the log-depth levels with one warp per comparison are cheapest; where they ran long
+            // (tiled / periodic text: up to 1 MiB per comparison) the work-efficient CTA-wide levels are 6x faster
+            bool hs_scan = g_tune_lyscan == 1;
+            if (g_tune_lyscan == 0 && ngroups > 1) {
+                rc = readback(ctx, st, small + 6, 4);
+                if (rc) return rc;
+                hs_scan = (u64)ctx->h_small[0] < 4ull * nch;  // under 4 KiB per comparison on average
+            }
+            if (hs_scan) {
                 // Hillis-Steele levels over the groups (round 1): ngroups log ngroups warp-wide comparisons
                 u32 *gin = group_min, *gout = group_alt;
                 for (u32 stride = 1; stride < ngroups; stride <<= 1) {

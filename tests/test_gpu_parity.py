@@ -668,7 +668,7 @@ def test_lyndon_scan_variants_agree(bwts, ctx, oracle, gen):
             want = oracle.forward(x)
             for chunk in (0, 64, 16):
                 bwts.tune(0, chunk)
-                for scan in (0, 1):
+                for scan in (0, 1, 2):
                     bwts.tune(17, scan)
                     assert ctx.forward_host(x) == want, (len(x), chunk, scan)
     finally:
