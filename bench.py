@@ -551,6 +551,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         dist = dist_mod
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side group: ranks that sit out a leg wait on the CPU -- an NCCL barrier would park a spinning
+        # kernel on their GPU while rank 0's dealer (another process) wants to run kernels on that same GPU
+        host_group = dist.new_group(backend="gloo")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     numa = pin_to_gpu_numa_node(torch, local_rank)
@@ -576,6 +579,11 @@ def run_gpu_arm(args, rank, local_rank, world):
         if dist:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def host_barrier():
+        torch.cuda.synchronize(dev)
+        if dist:
+            dist.barrier(group=host_group)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -622,6 +630,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     # own dealer (run_blocks: one host thread + pipeline per device); the other ranks wait
     dealer = None
     if world > 1 and args.workload in MULTI and not args.no_dealer:
+        host_barrier()  # every GPU is idle from here on; the other ranks wait in gloo, not on their GPU
         if rank == 0:
             allplan = [blk for r in range(world) for blk in plan_blocks(args.workload, r, world)]
             allplan.sort(key=lambda p: p[1])  # file order = block order = seed order
@@ -635,7 +644,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                              "multi-block file in pinned host memory, host clock around both calls; per-block SHA-256 of "
                              "the forward output compared with the unmodified reference's"}
             del items
-        barrier()
+        host_barrier()
 
     if rank == 0:
         peak, peak_src = measured_peak()
