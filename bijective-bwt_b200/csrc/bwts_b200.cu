@@ -213,6 +213,12 @@ static size_t workspace_bytes(size_t n)
 }
 
 static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+// look-back status of a re-rank over m slots: one word per tile + one per block of 32 tiles (forward.cuh)
+static inline size_t rr_status_bytes(u32 m)
+{
+    const size_t tiles = cdiv(m, RR_TILE);
+    return (tiles + tiles / 32 + 2) * 8;
+}
 static inline int bit_length(u64 v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
 
 // Counter read-backs go through a kernel that stores into mapped pinned memory, not through a
@@ -326,8 +332,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     u32 *cidx = arena_take<u32>(ctx, (size_t)nblk + 2);
     u8 *flags = arena_take<u8>(ctx, n);
     u32 *tilecnt = arena_take<u32>(ctx, ntl + 1);
-    u64 *rr_statusA = arena_take<u64>(ctx, rr_tiles + 1);
-    u64 *rr_statusB = arena_take<u64>(ctx, rr_tiles + 1);
+    u64 *rr_statusA = arena_take<u64>(ctx, rr_tiles + rr_tiles / 32 + 4);
+    u64 *rr_statusB = arena_take<u64>(ctx, rr_tiles + rr_tiles / 32 + 4);
     u32 *kS = arena_take<u32>(ctx, n);   // S set: key2 of the last warp-local sort
     u32 *vS = arena_take<u32>(ctx, n), *grpS = arena_take<u32>(ctx, n), *gstS = arena_take<u32>(ctx, n);
     // tuple set T (k_tuple_round): ring links by text position, double-buffered, + the rank increments
@@ -511,8 +517,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         CK(cudaMemsetAsync(rrc, 0, 2 * sizeof(RerankCounters), st));
         const LiveOut oS = {vS, grpS, gstS, nullptr};  // in place
         if (mS && sortedS) {
-            CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
-            CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
+            CK(cudaMemsetAsync(rr_statusA, 0, rr_status_bytes(mS), st));
+            CK(cudaMemsetAsync(rr_statusB, 0, rr_status_bytes(mS), st));
             if (t_on) {
                 LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<2, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
                        (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, nxtT[tc], tmax);
@@ -522,8 +528,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             }
         }
         if (mL && sortedL) {
-            CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
-            CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
+            CK(cudaMemsetAsync(rr_statusA, 0, rr_status_bytes(mL), st));
+            CK(cudaMemsetAsync(rr_statusB, 0, rr_status_bytes(mL), st));
             const LiveOut oL = {sb.v[sb.cur ^ 1], grp, gst, gid};  // grp / gst in place, idx into the idle half
             // First re-rank of a large input: all n ranks are written, at random text positions
             // (the kernel then runs at the DRAM random-access rate: 2.8 ms for 64 Mi elements, ncu:
@@ -601,16 +607,16 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             if (linear) return BWTS_B200_EINTERNAL;  // suffixes are pairwise distinct
             // ties are final: give every member of a tie its own slot
             if (mS) {
-                CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
-                CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mS, RR_TILE) * 8, st));
+                CK(cudaMemsetAsync(rr_statusA, 0, rr_status_bytes(mS), st));
+                CK(cudaMemsetAsync(rr_statusB, 0, rr_status_bytes(mS), st));
                 CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
                 LAUNCH(KC_RERANK, 16.0 * mS, (k_rerank<0, u32>), cdiv(mS, RR_TILE), RR_NT, (const u32 *)nullptr, vS,
                        grpS, gstS, mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc,
                        (u32 *)nullptr, (u32 *)nullptr, 0u);
             }
             if (mL) {
-                CK(cudaMemsetAsync(rr_statusA, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
-                CK(cudaMemsetAsync(rr_statusB, 0, (size_t)cdiv(mL, RR_TILE) * 8, st));
+                CK(cudaMemsetAsync(rr_statusA, 0, rr_status_bytes(mL), st));
+                CK(cudaMemsetAsync(rr_statusB, 0, rr_status_bytes(mL), st));
                 CK(cudaMemsetAsync(rrc + 1, 0, sizeof(RerankCounters), st));
                 LAUNCH(KC_RERANK, 16.0 * mL, (k_rerank<0, u64>), cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
                        sb.v[sb.cur], grp, gst, mL, 1, rank, none, (const u32 *)nullptr, none, rr_statusA,

@@ -428,26 +428,57 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
     }
 
     PH(19);  // scans
-    // ---- decoupled look-back on (max, sum, sum), by warp 0
+    // ---- decoupled look-back on (max, sum, sum, sum), by warp 0, over TWO levels of status words.
+    // With ~600 tiles in flight a one-level walk reads ~16 windows of 32 tile words before it meets a
+    // prefix (ncu: `barrier` 14-37 stalls per issue -- seven warps wait for this walk).  Here tiles form
+    // blocks of 32: a tile sums the words of its own block before it (one window), the last tile of a
+    // block publishes what the block adds, and the walk over earlier BLOCKS covers 1024 tiles per window:
+    // two or three L2 round trips in all.  Block words live behind the tile words (status[gridDim.x + block]).
     if (warp == 0) {
         u32 exh = 0, exs = 0, exl = 0, exg = 0;
-        if (tile == 0) {
-            if (lane == 0) {
-                st_relaxed_u64(statusB, rr_packB(RR_FLAG_PREFIX, totg, totl));
-                st_relaxed_u64(statusA, rr_packA(RR_FLAG_PREFIX, toth, tots));
+        u64 *blkA = statusA + gridDim.x, *blkB = statusB + gridDim.x;
+        const u32 blk = tile >> 5, r = tile & 31;
+        if (lane == 0) {
+            const u64 f = tile == 0 ? RR_FLAG_PREFIX : RR_FLAG_AGG;
+            st_relaxed_u64(statusB + tile, rr_packB(f, totg, totl));
+            st_relaxed_u64(statusA + tile, rr_packA(f, toth, tots));
+        }
+        bool done = tile == 0;  // the exclusive prefix is complete
+        if (!done && r > 0) {
+            // step 1: the tiles of my block before me, lane <-> tile 32 blk + lane
+            const u32 need = (1u << r) - 1;
+            const bool mine_ = lane < r;
+            for (;;) {
+                const u64 va = mine_ ? ld_relaxed_u64(statusA + blk * 32 + lane) : 0ull;
+                const u64 vb = mine_ ? ld_relaxed_u64(statusB + blk * 32 + lane) : 0ull;
+                const u32 fa = (u32)(va >> 62), fb = (u32)(vb >> 62);
+                const u32 flag = (fa == fb) ? fa : 0u;  // a tile counts once both of its words carry the same kind of flag
+                const u32 empties = __ballot_sync(FULL_MASK, mine_ && flag == 0);
+                const u32 prefixes = __ballot_sync(FULL_MASK, mine_ && flag == (u32)RR_FLAG_PREFIX);
+                u32 take = need;
+                if (prefixes) take &= ~((1u << (31 - __clz(prefixes))) - 1);  // from the prefix closest to me on
+                if (empties & take) continue;                                 // somebody in between has not published yet
+                const bool on = (take >> lane) & 1;
+                exh = warp_max(on ? (u32)((va >> 31) & 0x7fffffffu) : 0u);
+                exs = warp_sum(on ? (u32)(va & 0x7fffffffu) : 0u);
+                exl = warp_sum(on ? (u32)(vb & 0x7fffffffu) : 0u);
+                exg = warp_sum(on ? (u32)((vb >> 31) & 0x7fffffffu) : 0u);
+                done = prefixes != 0;  // a prefix word already holds everything before it
+                break;
             }
-        } else {
-            if (lane == 0) {
-                st_relaxed_u64(statusB + tile, rr_packB(RR_FLAG_AGG, totg, totl));
-                st_relaxed_u64(statusA + tile, rr_packA(RR_FLAG_AGG, toth, tots));
-            }
-            int t = (int)tile - 1;
+        }
+        if (!done && r == 31 && lane == 0) {  // what this block adds (if a prefix was met, the block's own prefix follows below)
+            st_relaxed_u64(blkB + blk, rr_packB(RR_FLAG_AGG, exg + totg, exl + totl));
+            st_relaxed_u64(blkA + blk, rr_packA(RR_FLAG_AGG, max(exh, toth), exs + tots));
+        }
+        if (!done && blk > 0) {
+            // step 2: the blocks before mine, 32 block words per window, until one carries a prefix
+            int t = (int)blk - 1;
             for (;;) {
                 const int q = t - (int)lane;
-                const u64 va = (q >= 0) ? ld_relaxed_u64(statusA + q) : rr_packA(RR_FLAG_PREFIX, 0, 0);
-                const u64 vb = (q >= 0) ? ld_relaxed_u64(statusB + q) : rr_packB(RR_FLAG_PREFIX, 0, 0);
+                const u64 va = (q >= 0) ? ld_relaxed_u64(blkA + q) : rr_packA(RR_FLAG_PREFIX, 0, 0);
+                const u64 vb = (q >= 0) ? ld_relaxed_u64(blkB + q) : rr_packB(RR_FLAG_PREFIX, 0, 0);
                 const u32 fa = (u32)(va >> 62), fb = (u32)(vb >> 62);
-                // a tile counts once both of its words carry the same kind of flag
                 const u32 flag = (fa == fb) ? fa : 0u;
                 const u32 empties = __ballot_sync(FULL_MASK, flag == 0);
                 const u32 prefixes = __ballot_sync(FULL_MASK, flag == (u32)RR_FLAG_PREFIX);
@@ -455,7 +486,7 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
                 if (prefixes) {
                     const u32 fp = __ffs(prefixes) - 1;
                     take = (fp == 31) ? FULL_MASK : ((2u << fp) - 1);
-                    if (empties & take) continue;  // a closer tile has not published yet
+                    if (empties & take) continue;  // a closer block has not published yet
                 } else {
                     if (empties) continue;
                     take = FULL_MASK;
@@ -468,12 +499,16 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
                 if (prefixes) break;
                 t -= 32;
             }
-            if (lane == 0) {
+        }
+        if (lane == 0) {
+            if (tile != 0) {
                 st_relaxed_u64(statusB + tile, rr_packB(RR_FLAG_PREFIX, exg + totg, exl + totl));
                 st_relaxed_u64(statusA + tile, rr_packA(RR_FLAG_PREFIX, max(exh, toth), exs + tots));
             }
-        }
-        if (lane == 0) {
+            if (r == 31) {  // the inclusive prefix of the last tile of a block is the block's
+                st_relaxed_u64(blkB + blk, rr_packB(RR_FLAG_PREFIX, exg + totg, exl + totl));
+                st_relaxed_u64(blkA + blk, rr_packA(RR_FLAG_PREFIX, max(exh, toth), exs + tots));
+            }
             s_exh = exh; s_exs = exs; s_exl = exl; s_exg = exg;
             if (tile == gridDim.x - 1) {  // the last tile's inclusive prefix = the totals
                 ctr->keptS = exs + tots;

@@ -37,5 +37,6 @@ int main(int argc, char **argv)
 		exit(1);
 	}
 	write_output(bwts, len, fp, "Write BWTS");
+	finish(fp);
 	return 0;
 }

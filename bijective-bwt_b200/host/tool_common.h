@@ -13,6 +13,7 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "../../include/bwts_b200.h"
 
@@ -51,6 +52,15 @@ static void print_timings(bwts_b200_ctx *ctx)
 }
 
 /* fwrite with the reference's last mark: "Write BWTS time" (/root/reference/mk_bwts_sa.c:60-62) */
+/* Leave without tearing the CUDA context down piece by piece (0.3-0.5 s with a 70 GB workspace): the
+ * output is flushed, the kernel reclaims everything else. */
+static void finish(FILE *fp)
+{
+	if (fp && fp != stdout) fclose(fp);
+	fflush(NULL);
+	_exit(0);
+}
+
 static void write_output(const unsigned char *data, long len, FILE *fp, const char *label)
 {
 	struct timespec t0, t1;

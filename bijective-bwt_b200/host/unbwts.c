@@ -47,5 +47,6 @@ int main(int argc, char **argv)
 	unsigned char *text = run_transform(1, BWTS, len);
 
 	write_out(text, len, outname, inname);
+	finish(NULL);
 	return 0;
 }
