@@ -1121,6 +1121,16 @@ static bwts_b200_ctx *g_dev_ctx[MAX_DEV];
 static int stage_h2d(bwts_b200_ctx *ctx, u8 *d_dst, const u8 *src, size_t len, cudaStream_t st);
 static int stage_d2h(bwts_b200_ctx *ctx, u8 *dst, const u8 *d_src, size_t len, cudaStream_t st);
 
+// The per-device context behind the one-call entry points and the block dealer: nobody can ask it for
+// statistics, so it records no per-launch events (two cudaEventRecord per kernel are a quarter of a
+// small transform's time: ~120 launches for a 1 MiB input).  BWTS_B200_PROFILE=1 switches them back on.
+static bwts_b200_ctx *create_default_ctx(int device)
+{
+    bwts_b200_ctx *ctx = bwts_b200_create(device);
+    if (ctx && !getenv("BWTS_B200_PROFILE") && !getenv("BWTS_B200_TRACE")) ctx->profile = false;
+    return ctx;
+}
+
 static int run_host(bwts_b200_ctx *ctx, int direction, const unsigned char *in, long len, unsigned char *out)
 {
     if (!ctx) return BWTS_B200_EINVAL;
@@ -1174,7 +1184,7 @@ static int with_default_ctx(int device, int direction, const unsigned char *in, 
     if (ndev == 0) return BWTS_B200_ENODEV;
     if (device < 0 || device >= ndev || device >= MAX_DEV) return BWTS_B200_EINVAL;
     std::lock_guard<std::mutex> lock(g_dev_mutex[device]);
-    if (!g_dev_ctx[device]) g_dev_ctx[device] = bwts_b200_create(device);
+    if (!g_dev_ctx[device]) g_dev_ctx[device] = create_default_ctx(device);
     if (!g_dev_ctx[device]) return BWTS_B200_ENODEV;
     return run_host(g_dev_ctx[device], direction, in, len, out);
 }
@@ -1345,7 +1355,7 @@ static int run_blocks_on_device(int direction, const u8 *in, long len, long bloc
     if (dev >= MAX_DEV) return BWTS_B200_EINVAL;
     // the device's cached context (and its workspace) serves all blocks of this call
     std::lock_guard<std::mutex> lock(g_dev_mutex[dev]);
-    if (!g_dev_ctx[dev]) g_dev_ctx[dev] = bwts_b200_create(dev);
+    if (!g_dev_ctx[dev]) g_dev_ctx[dev] = create_default_ctx(dev);
     bwts_b200_ctx *ctx = g_dev_ctx[dev];
     if (!ctx) return BWTS_B200_ENODEV;
     if (cudaSetDevice(dev) != cudaSuccess) return BWTS_B200_ECUDA;
@@ -1505,7 +1515,7 @@ extern "C" int bwts_b200_divsufsort(const unsigned char *T, int *SA, int n, int 
     if (ndev == 0) return BWTS_B200_ENODEV;
     if (device < 0 || device >= ndev || device >= MAX_DEV) return BWTS_B200_EINVAL;
     std::lock_guard<std::mutex> lock(g_dev_mutex[device]);
-    if (!g_dev_ctx[device]) g_dev_ctx[device] = bwts_b200_create(device);
+    if (!g_dev_ctx[device]) g_dev_ctx[device] = create_default_ctx(device);
     bwts_b200_ctx *ctx = g_dev_ctx[device];
     if (!ctx) return BWTS_B200_ENODEV;
     CK(cudaSetDevice(device));
