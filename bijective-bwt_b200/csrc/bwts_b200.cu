@@ -42,7 +42,7 @@ static long g_tune_onesweep = 0;   // onesweep tile configuration (see radix_sor
 static long g_tune_local = 0;      // 1 = never use the warp-local sort path
 static long g_tune_lyndon = 0;     // 1 = always take the suffix-sort fallback for the Lyndon boundaries
 static long g_tune_keybits = 0;    // cap on the bits of the initial packed key (0 = 64)
-static long g_tune_emit = 0;       // emit: 0 = binned from 512 Mi bytes, 1 = always rank windows, 2 = always binned
+static long g_tune_emit = 0;       // emit: 0 = packed-binned from 512 Mi bytes, 1 = always rank windows, 2 = always packed-binned, 3 = always binned as (rank, byte) pairs
 static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L set
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
@@ -739,9 +739,25 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     ctx->phase = PH_EMIT;
     (void)PH_SORT0;
     if (!linear) {
-        const bool emit_binned = g_tune_emit == 2 || (g_tune_emit == 0 && n >= (512u << 20));
-        if (emit_binned && kb >= 8) {
-            // (rank, byte) pairs binned by rank region, then scattered through L2; the sort buffers are idle
+        const bool emit_binned = g_tune_emit >= 2 || (g_tune_emit == 0 && n >= (512u << 20));
+        if (emit_binned && kb >= 8 && g_tune_emit != 3) {
+            // one packed word per element, binned by rank region, then scattered through L2: the bin pass reads
+            // rank[] and the text, the value T[i-1] rides in the bits above the in-bin part of the rank
+            u32 *packed = (u32 *)sb.k[0];
+            const u32 shift = kb - 8;
+            LAUNCH(KC_EMIT, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
+            do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
+            LaunchRec r__;
+            r__.cls = KC_EMIT; r__.bytes = 9.0 * n; r__.e0 = r__.e1 = nullptr; r__.name = "k_onesweep_pass<u32> pack";
+            if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
+            k_onesweep_pass<u32, 384, 12, 3, 4, 2><<<cdiv(n, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
+                rank, (const u32 *)dT, (u32 *)nullptr, packed, n, shift, sb.hist, sb.status, ctx->epoch);
+            if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
+            r__.phase = ctx->phase; ctx->recs.push_back(r__);
+            CK(cudaGetLastError());
+            LAUNCH(KC_EMIT, 5.0 * n, k_scatter_packed, cdiv(cdiv(n, 4), 256), 256, packed, n, shift, d_out);
+        } else if (emit_binned && kb >= 8) {
+            // (round 1, tune 9 = 3) (rank, byte) pairs as two u32 streams binned by rank region
             u32 *val = (u32 *)sb.k[0], *bin_pos = val + (((size_t)n + 3) & ~(size_t)3);
             u32 *bin_val = (u32 *)sb.k[1];
             const u32 shift = kb - 8;
@@ -1018,6 +1034,9 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     OS_ATTR(u64, 512, 8, 3, 8);
     OS_ATTR(u64, 256, 16, 3, 8);
     OS_ATTR(u32, 384, 12, 3, 4);
+    cudaFuncSetAttribute(k_onesweep_pass<u32, 384, 12, 3, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)OsSmem<u32, 384, 12>::bytes);
+    cudaFuncSetAttribute(k_onesweep_pass<u32, 384, 12, 3, 4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_local_sort_cta_radix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LsrSmem::bytes);
     cudaFuncSetAttribute(k_local_sort_cta_radix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LsrSmem::bytes);
     cudaFuncSetAttribute(k_local_sort_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LS_CAP * sizeof(u64)));

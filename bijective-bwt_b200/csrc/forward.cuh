@@ -1252,6 +1252,23 @@ __global__ void __launch_bounds__(256) k_scatter_bytes(const u32 *__restrict__ p
         for (u32 j = j0; j < n; j++) out[pos[j]] = (u8)val[j];
     }
 }
+// packed form of the same (k_onesweep_pass MODE 2): word j of the binned stream belongs to rank bin
+// j >> shift (the bins hold exactly 2^shift ranks each: the ranks are a permutation of 0..n-1)
+__global__ void __launch_bounds__(256) k_scatter_packed(const u32 *__restrict__ packed, u32 n, u32 shift,
+                                                        u8 *__restrict__ out)
+{
+    const u32 j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= n) return;
+    const u32 mask = (1u << shift) - 1u;
+    if (j0 + 4 <= n) {
+        const uint4 w = ldg_stream_u4((const uint4 *)(packed + j0));
+        const u32 ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) out[(((j0 + q) >> shift) << shift) | (ww[q] & mask)] = (u8)(ww[q] >> shift);
+    } else {
+        for (u32 j = j0; j < n; j++) out[((j >> shift) << shift) | (packed[j] & mask)] = (u8)(packed[j] >> shift);
+    }
+}
 // factor heads receive the last byte of their own factor
 __global__ void __launch_bounds__(256) k_emit_heads(const u8 *__restrict__ T, const u32 *__restrict__ FS, u32 F,
                                                     const u32 *__restrict__ rank, u8 *__restrict__ out)

@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256) k_inv_walk_stage(const u32 *__restrict__ 
             if (__all_sync(FULL_MASK, s == NONE32)) break;
         }
         if (s != NONE32) {
-            const u32 p = __ldg(prev + i);  // default L2 policy: evict-first hints cost 1.7x on arrays that partly fit L2 (tests/bench_gather.cu, 256 MiB)
+            const u32 p = ldg_stream_u32(prev + i);  // evict-first: keeps the reach marks resident in L2 (default policy: C5 block inverse 13.5 -> 14.7 ms)
             // who was reached?  Either one bit per element (n / 8 bytes: beyond ~512 MiB of input the
             // bitmap falls out of L2 and every mark becomes a DRAM read-modify-write) or one 8-bit
             // count per 128 elements (n / 128 bytes, L2-resident at every size; k_inv_find_deficient)
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(128) k_inv_walk_tail(const u32 *__restrict__ p
     if (d >= L) d -= L;
     u32 i = cont[s];
     do {
-        const u32 p = __ldg(prev + i);  // default L2 policy: evict-first hints cost 1.7x on arrays that partly fit L2 (tests/bench_gather.cu, 256 MiB)
+        const u32 p = ldg_stream_u32(prev + i);  // evict-first: keeps the reach marks resident in L2 (default policy: C5 block inverse 13.5 -> 14.7 ms)
         out[top - d] = (u8)byte_of_rank(sC, p);
         if (++d == L) d = 0;
         i = p;

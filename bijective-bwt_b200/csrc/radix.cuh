@@ -117,12 +117,21 @@ struct OsSmem {
 
 static __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
-template <typename K, int NT, int IPT, int MINB, int LB, bool ORACLE = false>
+// MODE 0: the sort pass.  MODE 1 (ORACLE): timing experiment, see below.  MODE 2 (PACK, u32 keys): the
+// binning pass of the large-output emit -- `vin` is the TEXT (bytes), the value of element i is
+// T[i - 1], and the only output is one packed word per element, (key & low bits) | byte << shift: inside
+// a rank bin the high bits of the rank are the bin number, which the position in the stream gives back
+// (k_scatter_packed).  14 bytes per element instead of 30 for the (rank, byte) pairs as two u32 streams.
+template <typename K, int NT, int IPT, int MINB, int LB, int MODE = 0>
 __global__ void __launch_bounds__(NT, MINB)
-k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__restrict__ kout,
+k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin_or_text, K *__restrict__ kout,
                   u32 *__restrict__ vout, u32 m, u32 shift, const u32 *__restrict__ binbase,
                   u64 *__restrict__ status, u32 epoch)
 {
+    constexpr bool ORACLE = MODE == 1, PACK = MODE == 2;
+    static_assert(!PACK || sizeof(K) == 4, "the packed emit pass bins 32-bit ranks");
+    const u32 *__restrict__ vin = PACK ? (const u32 *)nullptr : vin_or_text;
+    const u8 *__restrict__ text = (const u8 *)vin_or_text;
     using L = OsSmem<K, NT, IPT>;
     constexpr int TILE = L::TILE, NW = L::NW;
     static_assert(NT >= RADIX_BINS && TILE <= 65536 && IPT % 4 == 0, "one thread per digit; 16-bit tile positions");
@@ -293,8 +302,14 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin, K *__res
             const u32 p = s_inv[s];
             const K k = s_keys[p];
             const u32 dst = s + s_adj[(u32)(k >> shift) & (RADIX_BINS - 1)];
-            kout[dst] = k;
-            vout[dst] = vin ? s_vals[p] : base + p;
+            if (PACK) {
+                const u32 i = base + p;  // element index = text position; position 0 starts a factor (k_emit_heads)
+                const u32 byte = i ? (u32)text[i - 1] : 0u;
+                vout[dst] = ((u32)k & ((1u << shift) - 1u)) | (byte << shift);
+            } else {
+                kout[dst] = k;
+                vout[dst] = vin ? s_vals[p] : base + p;
+            }
         }
     }
     OS_PHASE(8);

@@ -146,8 +146,8 @@ const char *bwts_b200_version(void);
  * 5 = no copy/compute overlap between the blocks of one device (1), 6 = cap on the bits of
  * the initial packed key (8..64), 7 = binned rank scatter of the first re-rank (1 = never,
  * 2 = always; default: inputs of 4 Mi bytes and more), 8 = never sort the large-group set
- * CTA-locally (1), 9 = emit through rank windows (1) or binned by rank region (2; default:
- * binned from 512 Mi bytes), 10 = cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured: no
+ * CTA-locally (1), 9 = emit through rank windows (1), binned by rank region as one packed word per
+ * element (2; default from 512 Mi bytes) or as (rank, byte) pairs in two streams (3), 10 = cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured: no
  * effect), 12 = inverse through two read-only walks (1) instead of the staged single walk, 13 =
  * sublists per warp of the staged walk, 14 = largest group the text-ordered tuple set takes (1 =
  * set switched off, 2..32; default 8), 15 = inverse marks reached elements with one bit each (1) or one

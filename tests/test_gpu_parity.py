@@ -328,15 +328,18 @@ def test_cta_local_sort_path_and_radix_path_agree(bwts, ctx, oracle, gen):
 
 
 def test_binned_emit_forced_on_small_inputs(bwts, ctx, oracle, gen):
-    """emit as (rank, byte) pairs binned by rank region (default from 512 Mi bytes), forced here"""
-    bwts.tune(9, 2)
+    """emit binned by rank region (default from 512 Mi bytes), forced here: as one packed word per element
+    (tune 9 = 2: in-bin rank bits | byte, the bin pass reads the text itself) and as (rank, byte) pairs in two
+    u32 streams (3: round 1); rank windows (1) as the sibling"""
     try:
-        for n in (256, 257, 1000, 3073, 70_001):
-            for name, x in helpers.families(n).items():
-                assert ctx.forward_host(x) == oracle.forward(x), (name, n)
-        for kind, seed, n in (("text", 27, 3_000_001), ("dna", 28, 2_000_003), ("tiled", 29, 1_500_000)):
-            x = gen.make(kind, seed, n)
-            assert ctx.forward_host(x) == oracle.forward(x), kind
+        for mode in (2, 3, 1):
+            bwts.tune(9, mode)
+            for n in (256, 257, 1000, 3073, 4608, 4609, 70_001):
+                for name, x in helpers.families(n).items():
+                    assert ctx.forward_host(x) == oracle.forward(x), (name, n, mode)
+            for kind, seed, n in (("text", 27, 3_000_001), ("dna", 28, 2_000_003), ("tiled", 29, 1_500_000)):
+                x = gen.make(kind, seed, n)
+                assert ctx.forward_host(x) == oracle.forward(x), (kind, mode)
     finally:
         bwts.tune(9, 0)
 
