@@ -48,6 +48,7 @@ static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter w
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
 static long g_tune_ctasort = 0;    // CTA-local sort: 0 = radix in shared memory, 1 = bitonic network (round 1)
 static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = Hillis-Steele levels under a probe budget, else CTA-wide; 1 / 2 = force either
+static long g_tune_tmode = 0;      // tuple set: 0 = one thread per group (up to 32 members), 1 = one thread per member (up to 8)
 static long g_tune_tmax = 0;       // tuple set: largest group it takes (0 = 8, 1 = set switched off, 2..32)
 static long g_tune_invpath = 0;    // inverse: 0 = staged single walk (default), 1 = two read-only walks (round 1)
 static long g_tune_invq = 0;       // inverse staged walk: sublists per warp (0 = auto: one full wave of warps)
@@ -339,7 +340,10 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     // tuple set T (k_tuple_round): ring links by text position, double-buffered, + the rank increments
     // tune 14: 0 = groups of up to 8, switched on by what the first small-group round finds (below); 1 = off;
     // 2..32 = that size, on from the first re-rank (tests)
-    const u32 tmax = g_tune_local ? 1u : (g_tune_tmax == 0 ? 8u : (u32)g_tune_tmax);
+    // tune 20: 0 = one thread per group (k_tuple_round_heads, groups of up to 32), 1 = one thread per member (up to 8)
+    const bool theads = g_tune_tmode == 0;
+    const u32 thead = theads ? TUPLE_HEAD : 0u;
+    const u32 tmax = g_tune_local ? 1u : (g_tune_tmax == 0 ? (theads ? 32u : 8u) : (u32)g_tune_tmax);
     bool t_on = !g_tune_local && g_tune_tmax >= 2, t_decided = t_on || tmax < 2;
     u32 *nxtT[2] = {nullptr, nullptr};
     u8 *drT = nullptr;
@@ -521,10 +525,10 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             CK(cudaMemsetAsync(rr_statusB, 0, rr_status_bytes(mS), st));
             if (t_on) {
                 LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<2, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
-                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, nxtT[tc], tmax);
+                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, nxtT[tc], tmax, thead);
             } else {
                 LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<0, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
-                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, (u32 *)nullptr, 0u);
+                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
             }
         }
         if (mL && sortedL) {
@@ -541,11 +545,11 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             if (g_tune_local) {
                 LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<0, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oL, (const u32 *)nullptr, none,
-                       rr_statusA, rr_statusB, rrc + 1, nr_out, (u32 *)nullptr, 0u);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out, (u32 *)nullptr, 0u, 0u);
             } else {
                 LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<1, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL,
-                       rr_statusA, rr_statusB, rrc + 1, nr_out, t_on ? nxtT[tc] : (u32 *)nullptr, t_on ? tmax : 0u);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out, t_on ? nxtT[tc] : (u32 *)nullptr, t_on ? tmax : 0u, thead);
             }
         }
         if (mL && sortedL && first && use_binned_scatter(n, kb)) {
@@ -612,7 +616,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                 CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
                 LAUNCH(KC_RERANK, 16.0 * mS, (k_rerank<0, u32>), cdiv(mS, RR_TILE), RR_NT, (const u32 *)nullptr, vS,
                        grpS, gstS, mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc,
-                       (u32 *)nullptr, (u32 *)nullptr, 0u);
+                       (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
             }
             if (mL) {
                 CK(cudaMemsetAsync(rr_statusA, 0, rr_status_bytes(mL), st));
@@ -620,12 +624,17 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                 CK(cudaMemsetAsync(rrc + 1, 0, sizeof(RerankCounters), st));
                 LAUNCH(KC_RERANK, 16.0 * mL, (k_rerank<0, u64>), cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
                        sb.v[sb.cur], grp, gst, mL, 1, rank, none, (const u32 *)nullptr, none, rr_statusA,
-                       rr_statusB, rrc + 1, (u32 *)nullptr, (u32 *)nullptr, 0u);
+                       rr_statusB, rrc + 1, (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
             }
             if (mT) {  // members of a final tie take consecutive slots in text order, the rings dissolve
                 CK(cudaMemsetAsync(tcnt, 0, 16, st));
-                LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round<false>, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, FS, cidx,
-                       n, (u32)k, 1, tcnt);
+                if (theads) {
+                    LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round_heads<false>, tgrid * 2, TUPLE_HNT, nxtT[tc], nxtT[tc ^ 1], drT,
+                           rank, FS, cidx, n, (u32)k, 1, tcnt);
+                } else {
+                    LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round<false>, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, FS, cidx,
+                           n, (u32)k, 1, tcnt);
+                }
                 LAUNCH(KC_TUPLE, 4.0 * n + 13.0 * mT, k_tuple_apply, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, n);
             }
             break;
@@ -640,7 +649,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         if (mT) {
             // the tuple set first: phase A on old ranks and rings, phase B applies; the rank-ordered sets
             // gather afterwards (a group is refined as a whole, readers never see it at two depths)
-            if (!linear) {
+            if (theads && !linear) {
+                LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round_heads<false>, tgrid * 2, TUPLE_HNT, nxtT[tc], nxtT[tc ^ 1], drT,
+                       rank, FS, cidx, n, (u32)k, 0, tcnt);
+            } else if (theads) {
+                LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round_heads<true>, tgrid * 2, TUPLE_HNT, nxtT[tc], nxtT[tc ^ 1], drT,
+                       rank, FS, cidx, n, (u32)k, 0, tcnt);
+            } else if (!linear) {
                 LAUNCH(KC_TUPLE, 4.0 * n + 30.0 * mT, k_tuple_round<false>, tgrid, 256, nxtT[tc], nxtT[tc ^ 1], drT, rank, FS, cidx,
                        n, (u32)k, 0, tcnt);
             } else {
@@ -1631,6 +1646,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 15) { g_tune_invmark = value; return 0; }
     if (key == 17) { g_tune_lyscan = value; return 0; }
     if (key == 18) { g_tune_ctasort = value; return 0; }
+    if (key == 20) { g_tune_tmode = value; return 0; }
     if (key == 16) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invbudget = value; return 0; }
     if (key == 13) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invq = value; return 0; }
     return BWTS_B200_EINVAL;

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
                                                   const u32 *__restrict__ baseS, LiveOut outL,
                                                   u64 *__restrict__ statusA, u64 *__restrict__ statusB,
                                                   RerankCounters *__restrict__ ctr, u32 *__restrict__ nr_out,
-                                                  u32 *__restrict__ nxtT, u32 tmax)
+                                                  u32 *__restrict__ nxtT, u32 tmax, u32 head_flag)
 {
     __shared__ u32 s_all[MODE ? RR_TILE : 1];  // idx by tile slot (ring links of the tuple set)
     __shared__ u32 s_nt[RR_NT / 32];
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
                         // ring link: the next member in tile order, the head after the last one
                         nT++;
                         const u32 nx = (x + 1 < g_end) ? x + 1 : g_hs;
-                        nxtT[vi[q]] = s_all[MODE ? nx : 0];
+                        nxtT[vi[q]] = s_all[MODE ? nx : 0] | (x == g_hs ? head_flag : 0u);  // k_tuple_round_heads: the head does the group's work
                     } else {
                         nkhead += h;
                         kbits |= 1u << q;
@@ -803,7 +803,7 @@ static __device__ __forceinline__ void tuple_walk(const u32 *__restrict__ nxt_in
         less += kq < ki;
         diff |= kq != ki;
         if (kq == ki && eqn == NONE32) eqn = m;
-        m = __ldg(nxt_in + m);
+        m = __ldg(nxt_in + m) & ~0x80000000u;
     }
 }
 
@@ -866,6 +866,89 @@ __global__ void __launch_bounds__(256) k_tuple_round(const u32 *__restrict__ nxt
     }
     __syncthreads();
     if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(counters + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+// Phase A, one thread per GROUP (round 2b).  In the per-member form above every member walks the whole
+// ring: g^2 loads per group, which is why that form stops at 8 members.  Here the re-rank marks one member
+// of every ring (TUPLE_HEAD in its link word); the thread that sweeps over a marked position collects the
+// ring (g dependent link loads), gathers the g keys (independent), and writes the increment and the new
+// link of EVERY member: g loads per group, and groups of up to 32 can join the set (tmax 32), which takes
+// the warp-local sorts and their re-ranks out of the rounds of inputs with long repeats.  Locality is the
+// same: the heads of neighbouring rings are neighbours in the text, and so are their members.
+#define TUPLE_HEAD 0x80000000u
+#define TUPLE_CAP 32
+#define TUPLE_HNT 128
+template <bool LINEAR>
+__global__ void __launch_bounds__(TUPLE_HNT) k_tuple_round_heads(const u32 *__restrict__ nxt_in, u32 *__restrict__ nxt_out,
+                                                                 u8 *__restrict__ dr, const u32 *__restrict__ rank,
+                                                                 const u32 *__restrict__ FS, const u32 *__restrict__ cidx,
+                                                                 u32 n, u32 k, int finalize, u32 *__restrict__ counters)
+{
+    __shared__ u32 s_m[TUPLE_CAP][TUPLE_HNT], s_k[TUPLE_CAP][TUPLE_HNT];  // members / keys of my group, column = thread
+    __shared__ u32 s_cnt[3];
+    const u32 tid = threadIdx.x;
+    if (tid < 3) s_cnt[tid] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x * 4;
+    u32 remain = 0, split = 0, seen = 0;
+    for (u64 i64 = ((u64)blockIdx.x * blockDim.x + tid) * 4; i64 < n; i64 += stride) {
+        const u32 i0 = (u32)i64;
+        u32 v[4];
+        if (i64 + 4 <= n) {
+            const uint4 x = ldg_stream_u4((const uint4 *)(nxt_in + i0));
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = (i64 + q < n) ? nxt_in[i0 + q] : NONE32;
+        }
+        if ((v[0] & v[1] & v[2] & v[3]) == NONE32) continue;
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            if (v[q] == NONE32 || !(v[q] & TUPLE_HEAD)) continue;
+            const u32 i = i0 + q;
+            u32 g = 1, m = v[q] & ~TUPLE_HEAD;
+            s_m[0][tid] = i;
+            while (m != i && g < TUPLE_CAP) {
+                s_m[g][tid] = m;
+                g++;
+                m = __ldg(nxt_in + m) & ~TUPLE_HEAD;
+            }
+            for (u32 j = 0; j < g; j++) {
+                const u32 mj = s_m[j][tid];
+                s_k[j][tid] = finalize ? mj : tuple_key2<LINEAR>(rank, FS, cidx, n, k, mj);
+            }
+            for (u32 j = 0; j < g; j++) {
+                const u32 kj = s_k[j][tid];
+                u32 less = 0, diff = 0, after = NONE32, wrap = NONE32;
+                for (u32 l = 0; l < g; l++) {
+                    const u32 kl = s_k[l][tid];
+                    less += kl < kj;
+                    diff |= kl != kj;
+                    if (kl == kj && l != j) {
+                        if (l < j) { if (wrap == NONE32) wrap = l; }
+                        else if (after == NONE32) after = l;
+                    }
+                }
+                // the new ring of j's class keeps the collection order; its first member becomes the head
+                u32 nx = (after != NONE32) ? after : wrap;
+                if (finalize) nx = NONE32;
+                const u32 mj = s_m[j][tid];
+                nxt_out[mj] = (nx == NONE32) ? NONE32 : (s_m[nx][tid] | (wrap == NONE32 ? TUPLE_HEAD : 0u));
+                dr[mj] = (u8)less;
+                seen++;
+                remain += nx != NONE32;
+                split += diff;
+            }
+        }
+    }
+    remain = warp_sum(remain); split = warp_sum(split); seen = warp_sum(seen);
+    if (lane_id() == 0) {
+        if (remain) atomicAdd(&s_cnt[0], remain);
+        if (split) atomicAdd(&s_cnt[1], split);
+        if (seen) atomicAdd(&s_cnt[2], seen);
+    }
+    __syncthreads();
+    if (tid < 3 && s_cnt[tid]) atomicAdd(counters + tid, s_cnt[tid]);
 }
 
 __global__ void __launch_bounds__(256) k_tuple_apply(u32 *__restrict__ nxt_old, const u32 *__restrict__ nxt_new,

@@ -621,12 +621,15 @@ def test_tuple_set_sizes_agree(bwts, ctx, oracle, gen):
     try:
         for x in cases:
             want = oracle.forward(x)
-            seen = {}
-            for tmax in (1, 2, 0, 32):
-                bwts.tune(14, tmax)
-                assert ctx.forward_host(x) == want, (len(x), tmax)
-                seen[tmax] = ctx.stats()["tuple_rounds"]
-            assert seen[1] == 0
+            for tmode in (0, 1):   # one thread per group (rings marked with a head) / one thread per member
+                bwts.tune(20, tmode)
+                seen = {}
+                for tmax in (1, 2, 8, 32):
+                    bwts.tune(14, tmax)
+                    assert ctx.forward_host(x) == want, (len(x), tmode, tmax)
+                    seen[tmax] = ctx.stats()["tuple_rounds"]
+                assert seen[1] == 0
+        bwts.tune(20, 0)
         bwts.tune(14, 0)
         ctx.forward_host(cases[0])
         st = ctx.stats()
@@ -637,6 +640,7 @@ def test_tuple_set_sizes_agree(bwts, ctx, oracle, gen):
                 assert np.array_equal(bwts.suffix_array(x), oracle.suffix_array(x)), tmax
     finally:
         bwts.tune(14, 0)
+        bwts.tune(20, 0)
 
 
 def test_lyndon_suffix_sort_fallback(bwts, ctx, oracle, gen):
