@@ -48,7 +48,7 @@ static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter w
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
 static long g_tune_ctasort = 0;    // CTA-local sort: 0 = radix in shared memory, 1 = bitonic network (round 1)
 static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = Hillis-Steele levels under a probe budget, else CTA-wide; 1 / 2 = force either
-static long g_tune_tmode = 0;      // tuple set: 0 = one thread per group (up to 32 members), 1 = one thread per member (up to 8)
+static long g_tune_tmode = 0;      // tuple set: 0 = one thread per member (up to 8 members), 1 = one thread per group (up to 32)
 static long g_tune_tmax = 0;       // tuple set: largest group it takes (0 = 8, 1 = set switched off, 2..32)
 static long g_tune_invpath = 0;    // inverse: 0 = staged single walk (default), 1 = two read-only walks (round 1)
 static long g_tune_invq = 0;       // inverse staged walk: sublists per warp (0 = auto: one full wave of warps)
@@ -340,8 +340,9 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     // tuple set T (k_tuple_round): ring links by text position, double-buffered, + the rank increments
     // tune 14: 0 = groups of up to 8, switched on by what the first small-group round finds (below); 1 = off;
     // 2..32 = that size, on from the first re-rank (tests)
-    // tune 20: 0 = one thread per group (k_tuple_round_heads, groups of up to 32), 1 = one thread per member (up to 8)
-    const bool theads = g_tune_tmode == 0;
+    // tune 20: 0 = one thread per member (groups of up to 8), 1 = one thread per group (k_tuple_round_heads, up to
+    // 32; measured slower: C4 forward 287.8 ms against 276.9 -- half the lanes idle, the head's loads are serial)
+    const bool theads = g_tune_tmode == 1;
     const u32 thead = theads ? TUPLE_HEAD : 0u;
     const u32 tmax = g_tune_local ? 1u : (g_tune_tmax == 0 ? (theads ? 32u : 8u) : (u32)g_tune_tmax);
     bool t_on = !g_tune_local && g_tune_tmax >= 2, t_decided = t_on || tmax < 2;

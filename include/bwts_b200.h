@@ -154,7 +154,8 @@ const char *bwts_b200_version(void);
  * count per 128 (2; default: counts above 256 MiB), 16 = step budget of the inverse's fallback walks per attempt
  * (default 32 n), 17 = Lyndon chunk-minimum scan (1 = Hillis-Steele levels, 2 = CTA-wide levels; default:
  * chosen by the match lengths of the first level), 18 = CTA-local sort as the bitonic network of
- * round 1 (1) instead of the radix sort in shared memory.  value 0 = default.             */
+ * round 1 (1) instead of the radix sort in shared memory, 20 = tuple set with one thread per group and
+ * groups of up to 32 (1; measured slower than one thread per member).  value 0 = default. */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

@@ -621,7 +621,7 @@ def test_tuple_set_sizes_agree(bwts, ctx, oracle, gen):
     try:
         for x in cases:
             want = oracle.forward(x)
-            for tmode in (0, 1):   # one thread per group (rings marked with a head) / one thread per member
+            for tmode in (0, 1):   # one thread per member / one thread per group (rings marked with a head)
                 bwts.tune(20, tmode)
                 seen = {}
                 for tmax in (1, 2, 8, 32):
