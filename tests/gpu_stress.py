@@ -56,14 +56,24 @@ with bwts.Context(0) as ctx:
         shift = int(rng.choice([0, 0, 26, 28, 30, 31]))
         bwts.tune(0, chunk); bwts.tune(1, shift)
         bwts.tune(3, int(rng.random() < 0.15)); bwts.tune(4, int(rng.random() < 0.15))
+        # round-2 paths: binned scatter, CTA sort on/off + kind, emit form, inverse form + marks, tuple set size + form,
+        # Lyndon scan
+        knobs = {7: int(rng.choice([0, 0, 1, 2])), 8: int(rng.random() < 0.2), 9: int(rng.choice([0, 1, 2, 3])),
+                 12: int(rng.random() < 0.2), 14: int(rng.choice([0, 1, 2, 3, 8, 32])), 15: int(rng.choice([0, 1, 2])),
+                 17: int(rng.choice([0, 1, 2])), 18: int(rng.random() < 0.3), 20: int(rng.random() < 0.4)}
+        for key, val in knobs.items():
+            bwts.tune(key, val)
         wf, wi = oracle.forward(x), oracle.inverse(x)
         gf, gi = ctx.forward_host(x), ctx.inverse_host(x)
         cases += 1
-        if gf != wf or gi != wi or ctx.inverse_host(gf) != x:
+        sa_ok = True
+        if cases % 7 == 0 and len(x) > 1:
+            sa_ok = bool(np.array_equal(bwts.suffix_array(x), oracle.suffix_array(x)))
+        if gf != wf or gi != wi or not sa_ok or ctx.inverse_host(gf) != x:
             bad += 1
             Path("gpurun_out").mkdir(exist_ok=True)
             Path(f"gpurun_out/stress_fail_{bad}.bin").write_bytes(x)
-            print(f"MISMATCH {name} n={len(x)} chunk={chunk} shift={shift} fwd_ok={gf == wf} inv_ok={gi == wi}", flush=True)
+            print(f"MISMATCH {name} n={len(x)} chunk={chunk} shift={shift} knobs={knobs} fwd_ok={gf == wf} inv_ok={gi == wi} sa_ok={sa_ok}", flush=True)
             if bad >= 5:
                 break
 print(f"stress: {cases} cases, {bad} mismatches, seed {seed}")
