@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(256) k_build_keys(const u32 *__restrict__ idx,
 // size is taken from the tile's own head flags; a group that touches a tile border counts
 // as large -- that only costs speed, never correctness.
 #define RR_NT 256
+#ifndef RR_MINB
+#define RR_MINB 4  // CTAs per SM the re-rank is compiled for (64 registers at 4; experiments: -DRR_MINB=5 / 6)
+#endif
 #define RR_IPT 8
 #define RR_TILE (RR_NT * RR_IPT)
 #define RR_FLAG_AGG 1ull
@@ -233,7 +236,7 @@ struct LiveOut {  // one compaction stream
 // Tuple set: the members of a group are linked into a ring by text position, nxtT[idx] = idx of
 // the next member (k_tuple_round); they leave the rank-ordered arrays for good.
 template <int MODE, typename KeyT>
-__global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ keys, const u32 *idx,
+__global__ void __launch_bounds__(RR_NT, RR_MINB) k_rerank(const KeyT *__restrict__ keys, const u32 *idx,
                                                   const u32 *grp, const u32 *gst, u32 m,
                                                   int finalize, u32 *__restrict__ rank, LiveOut outS,
                                                   const u32 *__restrict__ baseS, LiveOut outL,
@@ -241,7 +244,11 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
                                                   RerankCounters *__restrict__ ctr, u32 *__restrict__ nr_out,
                                                   u32 *__restrict__ nxtT, u32 tmax, u32 head_flag)
 {
-    __shared__ u32 s_all[MODE ? RR_TILE : 1];  // idx by tile slot (ring links of the tuple set)
+    // compaction staging (outputs phase) -- and, before the look-back, st_idx doubles as `s_all`: idx by tile
+    // slot for the ring links of the tuple set (every thread is past the routing when the staging starts:
+    // two barriers lie between)
+    __shared__ u32 st_idx[RR_TILE], st_grp[RR_TILE], st_aux[RR_TILE], st_gid[RR_TILE];
+    u32 *s_all = st_idx;
     __shared__ u32 s_nt[RR_NT / 32];
     __shared__ __align__(16) u32 s_hw[RR_NT / 4 + 4];  // head flags of the tile as a bit array (slot = bit), + the slots after it
     __shared__ u32 s_sink[RR_NT];
@@ -525,7 +532,6 @@ __global__ void __launch_bounds__(RR_NT, 4) k_rerank(const KeyT *__restrict__ ke
     // changed ones.  Compaction: through shared memory, S members packed from slot 0, L members
     // behind them, so that both streams leave the tile with consecutive threads on consecutive
     // addresses (per-thread runs cost 32 four-byte transactions per store instruction).
-    __shared__ u32 st_idx[RR_TILE], st_grp[RR_TILE], st_aux[RR_TILE], st_gid[RR_TILE];
     u32 eh = __shfl_up_sync(FULL_MASK, ih, 1);
     u32 es = __shfl_up_sync(FULL_MASK, is, 1);
     u32 el = __shfl_up_sync(FULL_MASK, il, 1);
