@@ -3,7 +3,7 @@
 configurations at their full sizes -- C2 64 MiB text, C3 256 MiB tiled text, the 256 MiB
 Fibonacci word SURVEY 8(d) names as the C3 stress variant, C4 1 GiB DNA, the eight 256 MiB
 blocks of the C5 multi-block file (seeds 50..57), and C6, a 1.5 GiB DNA file above the 2^30
-limit of round 1 (the reference accepts any len < 2^31).
+limit of round 1, and C7, a DNA file of 2^31 - 1 bytes, the largest the reference accepts (len < 2^31).
 Run where /root/reference is mounted (C4 needs ~10 GiB of RAM and ~7 minutes, C6 ~15 GiB):
 
     python tests/golden/make_fullsize_golden.py [--only C5_0,C5_1,...] [--jobs 4]
@@ -30,7 +30,7 @@ import helpers  # noqa: E402
 CASES = [("C2", "text", 2, 64 << 20), ("C3", "tiled", 3, 256 << 20), ("C3F", "fibonacci", 0, 256 << 20),
          ("C4", "dna", 4, 1 << 30)]
 CASES += [(f"C5_{b}", "text", 50 + b, 256 << 20) for b in range(8)]
-CASES += [("C6", "dna", 6, 3 << 29)]
+CASES += [("C6", "dna", 6, 3 << 29), ("C7", "dna", 7, (1 << 31) - 1)]
 OUT = Path(__file__).parent / "fullsize.json"
 
 

@@ -161,6 +161,41 @@ def test_full_size_properties_c3_c4(bwts, gen, kind, seed, n):
         del back, y
 
 
+def test_largest_length_the_reference_accepts(gen):
+    """len = 2^31 - 1, the top of the reference's range (`int` / `saidx_t`): forward through the tools, SHA-256
+    against the unmodified reference's output where tests/golden/fullsize.json has it (C7: 17 minutes and 25 GB
+    of host memory for the reference), inverse back to the exact input.  157 GB of device workspace."""
+    import hashlib
+    import shutil
+    import tempfile
+    n = (1 << 31) - 1
+    gold = FULLSIZE.get("C7")
+    bindir = helpers.PKG / "bin"
+    td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        src, mid, back = (os.path.join(td, f) for f in ("in", "mid", "back"))
+        x = gen.make("dna", 7, n)
+        if gold:
+            assert gold["n"] == n and helpers.sha256(x) == gold["input_sha256"]
+        with open(src, "wb") as f:
+            f.write(x)
+        p = subprocess.run([str(bindir / "mk_bwts"), src, mid], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert os.path.getsize(mid) == n
+        if gold:
+            h = hashlib.sha256()
+            with open(mid, "rb") as f:
+                for blk in iter(lambda: f.read(1 << 24), b""):
+                    h.update(blk)
+            assert h.hexdigest() == gold["fwd_sha256"], "differs from the reference's mk_bwts output"
+        p = subprocess.run([str(bindir / "unbwts"), mid, back], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        with open(back, "rb") as f:
+            assert f.read() == x
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+
+
 def test_full_size_c6_above_2_30_through_the_tools(gen):
     """the reference accepts any len < 2^31 (mk_bwts_sa.c:26-27, unbwts.c:12-13): a 1.5 GiB DNA file goes through
     the drop-in tools, `bin/mk_bwts in out` then `bin/unbwts out back`; the forward file's SHA-256 equals
