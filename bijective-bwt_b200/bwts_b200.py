@@ -49,6 +49,7 @@ class Stats(ctypes.Structure):
         ("h2d_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double), ("lyndon_fallback", ctypes.c_int),
         ("phase_ms", ctypes.c_double * NPHASE), ("arena_bytes", ctypes.c_long), ("first_live", ctypes.c_long),
         ("tuple_rounds", ctypes.c_int), ("tuple_live_sum", ctypes.c_long), ("inverse_attempts", ctypes.c_int),
+        ("binned_rounds", ctypes.c_int),
     ]
 
 

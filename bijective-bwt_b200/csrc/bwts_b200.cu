@@ -70,7 +70,7 @@ static void apply_device_limits()
 static bool use_binned_scatter(unsigned n, unsigned kb)
 {
     if (g_tune_scatterbin == 1 || kb < 8) return false;
-    return g_tune_scatterbin == 2 || n >= (1u << 22);
+    return g_tune_scatterbin == 2 || g_tune_scatterbin == 4 || n >= (1u << 22);
 }
 
 struct LaunchRec { int cls; double bytes; cudaEvent_t e0, e1; const char *name = ""; int phase = 0; };
@@ -514,6 +514,8 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     u64 k = k0;
     const u32 kb = linear ? bit_length(n) : max(1, bit_length((u64)n - 1));
     bool first = true, sortedL = true;  // the L set enters the loop freshly sorted (initial sort)
+    bool binned_now = false;
+    u64 changedL = 0;  // estimate of the ranks the last L re-rank moved
     bool sortedS = false;
     const LiveOut none = {nullptr, nullptr, nullptr, nullptr};
     for (;;) {
@@ -541,7 +543,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             // 85 B moved per element).  Instead the ranks go out in sorted order, one u32 onesweep
             // pass bins the (position, rank) pairs by the top 8 bits of the position, and a
             // streaming kernel scatters them region by region through L2.
-            const bool binned = first && use_binned_scatter(n, kb);
+            // Later rounds of repetitive inputs (tiled text: every rotation stays live for 18 rounds) do the same
+            // once most ranks move again: at least half of the positions live and a third of the ranks changed in
+            // the round before.  Sparse sets gain nothing (one store per DRAM atom either way).
+            const bool binned = use_binned_scatter(n, kb) &&
+                                (first || g_tune_scatterbin == 4 ||
+                                 (g_tune_scatterbin != 3 && 2ull * mL >= n && 3ull * changedL >= mL));
+            binned_now = binned;
             u32 *nr_out = binned ? (u32 *)sb.k[sb.cur ^ 1] : (u32 *)nullptr;  // the idle key buffer: 8n bytes
             if (g_tune_local) {
                 LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<0, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
@@ -553,22 +561,29 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                        rr_statusA, rr_statusB, rrc + 1, nr_out, t_on ? nxtT[tc] : (u32 *)nullptr, t_on ? tmax : 0u, thead);
             }
         }
-        if (mL && sortedL && first && use_binned_scatter(n, kb)) {
-            // scratch: rank stream + binned positions in the idle key buffer, binned ranks in kS (the S set is still empty... its
-            // key2 array is first written by the warp-local sort of the coming round)
+        if (mL && sortedL && binned_now) {
+            // scratch: rank stream + binned positions in the idle key buffer, binned ranks in kS (the key2 array of the S
+            // set is dead between its re-rank above and the warp-local sort of the coming round, which writes it)
             u32 *nr_buf = (u32 *)sb.k[sb.cur ^ 1], *bin_pos = nr_buf + (((size_t)n + 3) & ~(size_t)3), *bin_val = kS;
             const u32 shift = kb - 8;
-            LAUNCH(KC_RERANK, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
+            if (mL == n) {
+                LAUNCH(KC_RERANK, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
+            } else {
+                CK(cudaMemsetAsync(sb.hist, 0, 256 * sizeof(u32), st));
+                LAUNCH(KC_RERANK, 4.0 * mL, k_bin_count, min(cdiv(cdiv(mL, 4), 256), 148u * 8u), 256, sb.v[sb.cur], mL, shift, sb.hist);
+                LAUNCH(KC_RERANK, 0, k_radix_hist_scan, 1, 256, sb.hist);
+            }
             do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
             LaunchRec r__;
-            r__.cls = KC_RERANK; r__.bytes = 16.0 * n; r__.e0 = r__.e1 = nullptr; r__.name = "k_onesweep_pass<u32> bin";
+            r__.cls = KC_RERANK; r__.bytes = 16.0 * mL; r__.e0 = r__.e1 = nullptr; r__.name = "k_onesweep_pass<u32> bin";
             if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
-            k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(n, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
-                sb.v[sb.cur], nr_buf, bin_pos, bin_val, n, shift, sb.hist, sb.status, ctx->epoch);
+            k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(mL, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
+                sb.v[sb.cur], nr_buf, bin_pos, bin_val, mL, shift, sb.hist, sb.status, ctx->epoch);
             if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
             r__.phase = ctx->phase; ctx->recs.push_back(r__);
             CK(cudaGetLastError());
-            LAUNCH(KC_RERANK, 12.0 * n, k_scatter_pairs, cdiv(cdiv(n, 8), 256), 256, bin_pos, bin_val, n, rank);
+            LAUNCH(KC_RERANK, 12.0 * mL, k_scatter_pairs, cdiv(cdiv(mL, 8), 256), 256, bin_pos, bin_val, mL, rank);
+            ctx->stats.binned_rounds++;
         }
         rc = readback(ctx, st, rrc, 2 * sizeof(RerankCounters) + 16);
         if (rc) return rc;
@@ -577,6 +592,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         // what the tuple round of the previous iteration left (zero when none ran) + this iteration's arrivals
         const u32 *tc_h = (const u32 *)((const RerankCounters *)ctx->h_small + 2);
         const bool splitT = tc_h[1] != 0;
+        changedL = 16ull * ((u64)cL.changed[0] + cL.changed[1] + cL.changed[2] + cL.changed[3]);
         u32 headsS = 0, headsL = 0, kheadsS = 0, kheadsL_all = 0, enteredT = 0;
         for (int q = 0; q < RR_SPREAD; q++) {
             headsS += cS.heads[q]; headsL += cL.heads[q];

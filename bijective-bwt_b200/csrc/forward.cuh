@@ -201,7 +201,8 @@ struct RerankCounters {
     u32 keptS;              // live elements compacted into the S stream
     u32 keptL;              // live elements compacted into the L stream
     u32 kheadsL;            // groups in the L stream
-    u32 pad[5];
+    u32 changed[4];         // ranks that changed, counted in every 16th tile (x 16 = estimate for the launch)
+    u32 pad[1];
     u32 keptT[RR_SPREAD];   // live elements handed to the tuple set (rings by text position)
 };
 
@@ -542,6 +543,7 @@ __global__ void __launch_bounds__(RR_NT, RR_MINB) k_rerank(const KeyT *__restric
     u32 ll = tots + offl + el;   // tile-local slot in the L stream, staged behind the S members
     u32 curg = s_exg + offg + eg;  // kept L heads up to and including the current slot
     u32 nrv[RR_IPT];
+    u32 nchg = 0;
 #pragma unroll
     for (int q = 0; q < RR_IPT; q++) {
         nrv[q] = 0;
@@ -551,6 +553,7 @@ __global__ void __launch_bounds__(RR_NT, RR_MINB) k_rerank(const KeyT *__restric
             const u32 jh = curh - 1;  // every slot has a head at or before it (slot gst[j] is one)
             const u32 nr = vg[q] + (jh - vs[q]);
             nrv[q] = nr;
+            nchg += nr != vg[q];
             if (!nr_out && nr != vg[q]) rank[vi[q]] = nr;
             if ((kbits >> q) & 1) {
                 u32 slot;
@@ -566,6 +569,10 @@ __global__ void __launch_bounds__(RR_NT, RR_MINB) k_rerank(const KeyT *__restric
                 st_aux[slot] = j - jh;  // distance to the group head: gst = own position - distance
             }
         }
+    }
+    if ((tile & 15) == 0) {  // how many ranks moved: the driver's cue for the binned scatter of the next round
+        const u32 c = warp_sum(nchg);
+        if (lane == 0 && c) atomicAdd(&ctr->changed[warp & 3], c);
     }
     if (nr_out) {
         if (full) {
@@ -1380,6 +1387,22 @@ __global__ void k_bin_bases(u32 n, u32 shift, u32 *__restrict__ base)
 {
     const u64 start = (u64)threadIdx.x << shift;  // 256 threads
     base[threadIdx.x] = (u32)min(start, (u64)n);
+}
+// later rounds: not every position is live, the bins are counted (then scanned by k_radix_hist_scan)
+__global__ void __launch_bounds__(256) k_bin_count(const u32 *__restrict__ pos, u32 m, u32 shift, u32 *__restrict__ hist)
+{
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 m4 = m / 4;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m4; j += gridDim.x * blockDim.x) {
+        const uint4 p = ldg_stream_u4((const uint4 *)pos + j);
+        atomicAdd(&h[p.x >> shift], 1u); atomicAdd(&h[p.y >> shift], 1u);
+        atomicAdd(&h[p.z >> shift], 1u); atomicAdd(&h[p.w >> shift], 1u);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (m & 3u)) atomicAdd(&h[pos[m4 * 4 + threadIdx.x] >> shift], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
 // rank[pos[j]] = val[j] over pairs that are grouped by text region: the targets of the CTAs
 // running at any one time fall into a few MiB, so the 4-byte stores merge in L2

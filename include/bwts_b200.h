@@ -125,6 +125,7 @@ typedef struct {
     int    tuple_rounds;        /* forward: rounds in which the text-ordered tuple set ran   */
     long   tuple_live_sum;      /* forward: sum over those rounds of its members             */
     int    inverse_attempts;    /* inverse: 1 + restarts with another splitter hash (fallback over budget) */
+    int    binned_rounds;       /* forward: re-ranks whose ranks went out through the binned scatter */
 } bwts_b200_stats;
 
 int bwts_b200_get_stats(const bwts_b200_ctx *ctx, bwts_b200_stats *out);
@@ -144,8 +145,9 @@ const char *bwts_b200_version(void);
  * (density 2^-(32-shift), 20..31), 2 = onesweep tile shape (0..4), 3 = disable the
  * warp-local sort path (1), 4 = force the suffix-sort fallback for the Lyndon boundaries (1),
  * 5 = no copy/compute overlap between the blocks of one device (1), 6 = cap on the bits of
- * the initial packed key (8..64), 7 = binned rank scatter of the first re-rank (1 = never,
- * 2 = always; default: inputs of 4 Mi bytes and more), 8 = never sort the large-group set
+ * the initial packed key (8..64), 7 = binned rank scatter of the re-ranks (1 = never, 2 = the first
+ * re-rank of inputs of any size, 3 = the first re-rank only, 4 = every re-rank of the large-group set; default:
+ * inputs of 4 Mi bytes and more, the first re-rank and later ones that move the ranks of a dense set), 8 = never sort the large-group set
  * CTA-locally (1), 9 = emit through rank windows (1), binned by rank region as one packed word per
  * element (2; default from 512 Mi bytes) or as (rank, byte) pairs in two streams (3), 10 = cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured: no
  * effect), 12 = inverse through two read-only walks (1) instead of the staged single walk, 13 =

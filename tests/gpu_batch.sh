@@ -1,13 +1,10 @@
 #!/bin/bash
 # One gpurun call's worth of measurements (scratch output under gpurun_out/); edited per call.
 # Every command runs under its own timeout: a hung kernel must not eat the box's time limit.
-out=gpurun_out/r2u; mkdir -p $out
-timeout 700 python -m pytest tests -m gpu -x -q > $out/pytest.txt 2>&1; echo "pytest rc=$?" >> $out/pytest.txt
-timeout 500 python bench.py > $out/bench_c4.json 2> $out/bench_c4.err; echo "bench rc=$?" >> $out/bench_c4.err
-M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
-for wl in C4 C3 C2; do
-  P="python tests/gpu_profile_target.py $wl"
-  timeout 120 $P > $out/plain_$wl.log 2>&1 && timeout 400 ncu --metrics $M --clock-control none --csv --log-file $out/launches_$wl.csv $P > $out/ncu_list_$wl.log 2>&1
-done
-python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.txt 2>&1; echo "smoke rc=$?" >> $out/smoke.txt
-tail -3 $out/pytest.txt; tail -2 $out/bench_c4.err; tail -2 $out/smoke.txt; cat $out/plain_*.log
+out=gpurun_out/r2v; mkdir -p $out
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "binned or cta or largest_length" > $out/pytest.txt 2>&1; echo "pytest rc=$?" >> $out/pytest.txt
+timeout 200 python tests/gpu_experiments.py C3 base 7:3 6:56 > $out/exp_c3.txt 2>&1
+timeout 200 python tests/gpu_experiments.py C4 base 7:3 6:40 6:48 6:56 > $out/exp_c4.txt 2>&1
+timeout 100 python tests/gpu_experiments.py C2 base 7:3 6:48 6:56 > $out/exp_c2.txt 2>&1
+timeout 200 python tests/gpu_experiments.py C3F base 7:3 > $out/exp_c3f.txt 2>&1
+tail -3 $out/pytest.txt; grep "^==" $out/exp_*.txt

@@ -58,7 +58,7 @@ with bwts.Context(0) as ctx:
         bwts.tune(3, int(rng.random() < 0.15)); bwts.tune(4, int(rng.random() < 0.15))
         # round-2 paths: binned scatter, CTA sort on/off + kind, emit form, inverse form + marks, tuple set size + form,
         # Lyndon scan
-        knobs = {7: int(rng.choice([0, 0, 1, 2])), 8: int(rng.random() < 0.2), 9: int(rng.choice([0, 1, 2, 3])),
+        knobs = {7: int(rng.choice([0, 0, 1, 2, 4, 4])), 8: int(rng.random() < 0.2), 9: int(rng.choice([0, 1, 2, 3])),
                  12: int(rng.random() < 0.2), 14: int(rng.choice([0, 1, 2, 3, 8, 32])), 15: int(rng.choice([0, 1, 2])),
                  17: int(rng.choice([0, 1, 2])), 18: int(rng.random() < 0.3), 20: int(rng.random() < 0.4)}
         for key, val in knobs.items():

@@ -163,12 +163,15 @@ def test_full_size_properties_c3_c4(bwts, gen, kind, seed, n):
 
 def test_largest_length_the_reference_accepts(gen):
     """len = 2^31 - 1, the top of the reference's range (`int` / `saidx_t`): forward through the tools, SHA-256
-    against the unmodified reference's output where tests/golden/fullsize.json has it (C7: 17 minutes and 25 GB
+    against the unmodified reference's output where tests/golden/fullsize.json has it (C7: 16 minutes and 21 GB
     of host memory for the reference), inverse back to the exact input.  157 GB of device workspace."""
     import hashlib
     import shutil
     import tempfile
+    import torch
     n = (1 << 31) - 1
+    if torch.cuda.mem_get_info(0)[0] < 73 * n + (1 << 28):
+        pytest.skip("needs 157 GB of free device memory")
     gold = FULLSIZE.get("C7")
     bindir = helpers.PKG / "bin"
     td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
@@ -328,6 +331,39 @@ def test_binned_rank_scatter_forced_on_small_inputs(bwts, ctx, oracle, gen):
     try:
         x = gen.make("dna", 26, 5_000_000)
         assert ctx.forward_host(x) == oracle.forward(x)
+    finally:
+        bwts.tune(7, 0)
+
+
+def test_binned_rank_scatter_in_later_rounds(bwts, ctx, oracle, gen):
+    """re-ranks after the first one also send their ranks through the bin pass once a dense large-group set moves
+    most of its ranks (tiled text: every rotation stays live for many rounds); tune 7 = 4 forces it for every
+    re-rank of the large-group set so that small and sparse sets cross the counted-bin path too, 3 keeps it to the
+    first re-rank (round 2 behaviour)"""
+    fam = helpers.families(70_001)
+    cases = [gen.make("tiled", 90, 6_000_000), helpers.fibonacci_word(5_000_000), gen.make("dna", 91, 4_500_000),
+             gen.make("text", 92, 4_200_000), fam["ww"], fam["runs"], fam["thue_morse"], fam["random2"],
+             (b"abcab" * 50_000) + b"b", bytes(1000), b"ab" * 130]
+    want = [oracle.forward(x) for x in cases]
+    try:
+        for mode in (4, 3, 0):
+            bwts.tune(7, mode)
+            later = 0
+            for x, w in zip(cases, want):
+                assert ctx.forward_host(x) == w, (mode, len(x))
+                later += max(0, ctx.stats()["binned_rounds"] - 1)
+            if mode == 4:
+                assert later >= 10, "forced: the later re-ranks must have used the bin pass"
+            if mode == 3:
+                assert later == 0
+            if mode == 0:
+                # default rule on the 6 MB tiled text: dense set + most ranks moving -> some later rounds binned
+                assert ctx.forward_host(cases[0]) == want[0]
+                assert ctx.stats()["binned_rounds"] >= 2, ctx.stats()
+        # linear mode (suffix array) through the same path
+        bwts.tune(7, 4)
+        x = cases[0][:1_500_000]
+        assert np.array_equal(bwts.suffix_array(x), oracle.suffix_array(x))
     finally:
         bwts.tune(7, 0)
 
