@@ -46,6 +46,7 @@ static long g_tune_emit = 0;       // emit: 0 = packed-binned from 512 Mi bytes,
 static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L set
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
+static long g_tune_hist = 0;       // 1 = digit histograms of the initial sort by k_radix_hist (eight shared atomics per key)
 static long g_tune_ctasort = 0;    // CTA-local sort: 0 = radix in shared memory, 1 = bitonic network (round 1)
 static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = Hillis-Steele levels under a probe budget, else CTA-wide; 1 / 2 = force either
 static long g_tune_tmode = 0;      // tuple set: 0 = one thread per member (up to 8 members), 1 = one thread per group (up to 32)
@@ -140,6 +141,17 @@ static cudaError_t launch_check(const char *name, cudaStream_t st)
         r__.cls = (KCLS_); r__.bytes = (double)(NBYTES_); r__.e0 = r__.e1 = nullptr; r__.name = #kern; \
         if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); } \
         kern<<<(grid), (block), 0, st>>>(__VA_ARGS__);                               \
+        if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
+        r__.phase = ctx->phase; ctx->recs.push_back(r__);                                                    \
+        CK(launch_check(#kern, st));                                                 \
+    } while (0)
+
+#define LAUNCH_SMEM(KCLS_, NBYTES_, kern, grid, block, smem_, ...)                   \
+    do {                                                                             \
+        LaunchRec r__;                                                               \
+        r__.cls = (KCLS_); r__.bytes = (double)(NBYTES_); r__.e0 = r__.e1 = nullptr; r__.name = #kern; \
+        if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); } \
+        kern<<<(grid), (block), (smem_), st>>>(__VA_ARGS__);                         \
         if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); } \
         r__.phase = ctx->phase; ctx->recs.push_back(r__);                                                    \
         CK(launch_check(#kern, st));                                                 \
@@ -354,10 +366,11 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         drT = arena_take<u8>(ctx, n);
         if (!nxtT[0] || !nxtT[1] || !drT) return BWTS_B200_EINTERNAL;
     }
+    u32 *whist = arena_take<u32>(ctx, 4096);  // histogram of the leading symbols of the initial keys (k_init_keys)
     u32 *small = arena_take<u32>(ctx, 1024);  // [0] F, [1] lmax, [2] sigma, [8..15] presence, [16..] rerank counters
     u8 *code = (u8 *)arena_take<u32>(ctx, 64);
     if (!sb.k[0] || !sb.k[1] || !sb.v[0] || !sb.v[1] || !sb.hist || !sb.status || !grp || !gst || !gid || !rank || !FS ||
-        !cidx || !flags || !tilecnt || !rr_statusA || !rr_statusB || !small || !code || !kS || !vS || !grpS || !gstS)
+        !cidx || !flags || !tilecnt || !rr_statusA || !rr_statusB || !small || !whist || !code || !kS || !vS || !grpS || !gstS)
         return BWTS_B200_EINTERNAL;
     RerankCounters *rrc = (RerankCounters *)(small + 16);
     u32 *tcnt = (u32 *)(rrc + 2);  // tuple round: [0] still in the set, [1] saw a split, [2] processed; read back with rrc
@@ -477,13 +490,24 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     ctx->stats.alphabet_bits = (int)bits;
     ctx->stats.initial_depth = (int)k0;
 
+    // digit histograms of the initial sort from one histogram of the leading symbols (k_init_keys): possible when the
+    // widest digit spans symbols worth at most 12 bits (alphabets of 1-4, 6 and 8 bits per symbol)
+    u32 wsyms = 0;
+    for (int p = 0; p < P0; p++) {
+        const u32 lo_bit = 8u * p, hi_bit = min(8u * p + 7u, k0 * bits - 1u);
+        wsyms = max(wsyms, hi_bit / bits - lo_bit / bits + 1u);
+    }
+    const bool use_wh = !linear && g_tune_hist != 1 && wsyms * bits <= 12 && k0 >= wsyms;
+    const u32 wbins = use_wh ? 1u << (wsyms * bits) : 0u;
     if (!linear) {
-        LAUNCH(KC_INIT_KEYS, 9.0 * n, k_init_keys, cdiv(cdiv(n, 8), 256), 256, dT, n, FS, cidx, code, bits, k0,
-               sb.k[0]);
+        if (use_wh) CK(cudaMemsetAsync(whist, 0, wbins * sizeof(u32), st));
+        LAUNCH_SMEM(KC_INIT_KEYS, 9.0 * n, k_init_keys, min(cdiv(n, 2048), (u32)ctx->sm_count * 6u), 256, wbins * sizeof(u32), dT, n,
+                    FS, cidx, code, bits, k0, sb.k[0], use_wh ? whist : (u32 *)nullptr, bits * (k0 - min(k0, wsyms)), wbins);
     } else {
         LAUNCH(KC_INIT_KEYS, 9.0 * n, k_init_keys_linear, cdiv(cdiv(n, 8), 256), 256, dT, n, code, bits, k0, sb.k[0]);
     }
-    rc = radix_sort(ctx, st, sb, n, P0, true, false);
+    if (use_wh) LAUNCH(KC_RADIX_HIST, 4.0 * wbins * P0, k_digit_hists, P0, 256, whist, wbins, wsyms, bits, k0, sb.hist);
+    rc = radix_sort(ctx, st, sb, n, P0, true, use_wh);
     if (rc) return rc;
 
     CK(cudaMemsetAsync(rank, 0, (size_t)n * 4, st));
@@ -1015,7 +1039,9 @@ static int inverse_core(bwts_b200_ctx *ctx, const u8 *dB, u32 n, u8 *d_out, cuda
     // again with another multiplier -- and four times the splitter density where the workspace has
     // room for it -- the last attempt unbounded.
     static const u32 muls[4] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu};
-    u32 shift = g_tune_spl_shift ? (u32)g_tune_spl_shift : 26u;
+    // one splitter per 64 elements; per 128 from 256 MiB on, where the 2 x 26 pointer-jumping rounds over the sublists
+    // cost more than the longer sublists do (C4 inverse 57.1 -> 49.5 ms with 512-byte slots, C5 block 13.6 -> 13.2 ms; C2: 3.79 -> 4.25 ms)
+    u32 shift = g_tune_spl_shift ? (u32)g_tune_spl_shift : (n >= (1u << 28) ? 25u : 26u);
     ctx->stats.inverse_attempts = 0;
     for (int a = 0; a < 4; a++) {
         ctx->arena_used = 0;
@@ -1664,6 +1690,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 17) { g_tune_lyscan = value; return 0; }
     if (key == 18) { g_tune_ctasort = value; return 0; }
     if (key == 20) { g_tune_tmode = value; return 0; }
+    if (key == 21) { g_tune_hist = value; return 0; }
     if (key == 16) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invbudget = value; return 0; }
     if (key == 13) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invq = value; return 0; }
     return BWTS_B200_EINVAL;

@@ -48,38 +48,100 @@ __global__ void k_code_table(const u32 *__restrict__ present, u8 *__restrict__ c
 
 // ---- initial keys: k0 packed symbols of the rotation starting at i -------------------------
 // Thread owns 8 consecutive positions; inside one factor and away from its end the window
-// slides by one symbol per position.
+// slides by one symbol per position.  The keys leave through shared memory: a thread storing its own
+// eight keys one by one puts 32 lanes on 32 different sectors per store instruction (ncu: 5.4 ms for the
+// 8 GiB of keys of C4, the L2 transaction rate); staged, consecutive lanes write consecutive 16 bytes.
+// rows of 8 keys + 1 pad word pair: the 64-byte stride of the thread rows would put 16 lanes on one bank pair
+#define IK_SLOT(l_) ((l_) + ((l_) >> 3))
+#define IK_WORDS (2048 + 256)
+static __device__ __forceinline__ void init_keys_flush(const u64 *s_keys, u64 *__restrict__ keys, u32 base, u32 n)
+{
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const u32 t = q * 256 + threadIdx.x;
+        if (base + t < n) keys[base + t] = s_keys[IK_SLOT(t)];
+    }
+}
+// Digit histograms of the initial sort without eight shared atomics per key (k_radix_hist: 7.7 ms at 1 GiB, exactly
+// the 4 lanes per clock and SM that ATOMS sustains; copies per lane group changed nothing).  A radix digit of the
+// packed key is a bit slice of w consecutive symbols, w = 2..4 -- and the symbols t .. t+w-1 of rotation i are the
+// first w symbols of rotation i + t (cyclic inside the factor): over all i of a factor that is every rotation once.
+// So ONE histogram of the leading w symbols (`whist`, 2^(w * bits) <= 4096 bins, one shared atomic per key, taken here
+// while the key is in a register) holds all eight digit histograms; k_digit_hists reads them off.
+// Grid-stride over tiles of 2048 positions: the window histogram is flushed once per CTA.
 __global__ void __launch_bounds__(256) k_init_keys(const u8 *__restrict__ T, u32 n, const u32 *__restrict__ FS,
                                                    const u32 *__restrict__ cidx, const u8 *__restrict__ code,
-                                                   u32 bits, u32 k0, u64 *__restrict__ keys)
+                                                   u32 bits, u32 k0, u64 *__restrict__ keys, u32 *__restrict__ whist,
+                                                   u32 wshift, u32 wbins)
 {
+    extern __shared__ u32 s_wh[];  // wbins words when whist != nullptr
     __shared__ u8 s_code[256];
+    __shared__ u64 s_keys[IK_WORDS];
     s_code[threadIdx.x] = code[threadIdx.x];
+    if (whist)
+        for (u32 b = threadIdx.x; b < wbins; b += 256) s_wh[b] = 0;
     __syncthreads();
-    const u32 i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    if (i0 >= n) return;
-    const u32 iend = min(n, i0 + 8);
+    const u32 l0 = threadIdx.x * 8;
     const u64 mask = (k0 * bits >= 64) ? ~0ull : ((1ull << (k0 * bits)) - 1);
-    u32 i = i0;
-    while (i < iend) {
-        const u32 f = factor_of(FS, cidx, i);
-        const u32 s = FS[f], e = FS[f + 1];
-        // first key of this stretch, symbol by symbol with cyclic wrap
-        u64 key = 0;
-        u32 pos = i;
-        for (u32 c = 0; c < k0; c++) {
-            key = (key << bits) | s_code[T[pos]];
-            pos = (pos + 1 == e) ? s : pos + 1;
-        }
-        keys[i] = key;
-        i++;
-        // slide while the window [i, i+k0) stays inside the factor
-        while (i < iend && i < e && (u64)i + k0 <= e) {
-            key = ((key << bits) | s_code[T[i + k0 - 1]]) & mask;
-            keys[i] = key;
+    const u32 ntiles = (n + 2047u) / 2048u;
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u32 i0 = tile * 2048u + l0;
+        const u32 iend = min(n, i0 + 8);
+        u32 i = i0;
+        while (i < iend) {
+            const u32 f = factor_of(FS, cidx, i);
+            const u32 s = FS[f], e = FS[f + 1];
+            // first key of this stretch, symbol by symbol with cyclic wrap
+            u64 key = 0;
+            u32 pos = i;
+            for (u32 c = 0; c < k0; c++) {
+                key = (key << bits) | s_code[T[pos]];
+                pos = (pos + 1 == e) ? s : pos + 1;
+            }
+            s_keys[IK_SLOT(l0 + (i - i0))] = key;
+            if (whist) atomicAdd(&s_wh[(u32)(key >> wshift)], 1u);
             i++;
+            // slide while the window [i, i+k0) stays inside the factor
+            while (i < iend && i < e && (u64)i + k0 <= e) {
+                key = ((key << bits) | s_code[T[i + k0 - 1]]) & mask;
+                s_keys[IK_SLOT(l0 + (i - i0))] = key;
+                if (whist) atomicAdd(&s_wh[(u32)(key >> wshift)], 1u);
+                i++;
+            }
+        }
+        init_keys_flush(s_keys, keys, tile * 2048u, n);
+        __syncthreads();  // the staging rows are free again
+    }
+    if (whist) {
+        for (u32 b = threadIdx.x; b < wbins; b += 256) {
+            const u32 c = s_wh[b];
+            if (c) atomicAdd(whist + b, c);
         }
     }
+}
+// ghist[p][d] = sum of whist[W] over the windows W whose slice for digit p is d.  Digit p = key bits [8p, 8p + 8);
+// symbol t of the key sits at bits [bits * (k0-1-t), bits * (k0-t)).  With t_lo / t_hi the symbols holding the lowest
+// / highest key bit of the digit (clipped to the key width), the digit is a slice of the first t_lo - t_hi + 1 symbols
+// of the window.  One block per digit.
+__global__ void __launch_bounds__(256) k_digit_hists(const u32 *__restrict__ whist, u32 wbins, u32 wsyms, u32 bits, u32 k0,
+                                                     u32 *__restrict__ ghist)
+{
+    __shared__ u32 sh[256];
+    const u32 p = blockIdx.x;
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 lo_bit = 8 * p, hi_bit = min(8 * p + 7, k0 * bits - 1);
+    const u32 t_lo = k0 - 1 - lo_bit / bits, t_hi = k0 - 1 - hi_bit / bits;
+    const u32 wp = t_lo - t_hi + 1;                   // symbols the digit touches (<= wsyms)
+    const u32 drop = bits * (wsyms - wp);             // trailing symbols of the window the digit does not see
+    const u32 sh_r = lo_bit - bits * (k0 - 1 - t_lo);  // digit's lowest bit inside symbol t_lo
+    for (u32 w = threadIdx.x; w < wbins; w += 256) {
+        const u32 c = whist[w];
+        if (c) atomicAdd(&sh[((w >> drop) >> sh_r) & 255u], c);
+    }
+    __syncthreads();
+    ghist[p * 256 + threadIdx.x] = sh[threadIdx.x];
 }
 
 // suffix-array variant: no factors, symbols are code+1, positions past the end read as 0
@@ -87,23 +149,27 @@ __global__ void __launch_bounds__(256) k_init_keys_linear(const u8 *__restrict__
                                                           u32 bits, u32 k0, u64 *__restrict__ keys)
 {
     __shared__ u8 s_code[256];
+    __shared__ u64 s_keys[IK_WORDS];
     s_code[threadIdx.x] = code[threadIdx.x];
     __syncthreads();
-    const u32 i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    if (i0 >= n) return;
-    const u32 iend = min(n, i0 + 8);
-    const u64 mask = (k0 * bits >= 64) ? ~0ull : ((1ull << (k0 * bits)) - 1);
-    u64 key = 0;
-    for (u32 c = 0; c < k0; c++) {
-        const u64 p = (u64)i0 + c;
-        key = (key << bits) | (p < n ? (u64)s_code[T[p]] + 1 : 0ull);
+    const u32 l0 = threadIdx.x * 8;
+    const u32 i0 = blockIdx.x * 2048u + l0;
+    if (i0 < n) {
+        const u32 iend = min(n, i0 + 8);
+        const u64 mask = (k0 * bits >= 64) ? ~0ull : ((1ull << (k0 * bits)) - 1);
+        u64 key = 0;
+        for (u32 c = 0; c < k0; c++) {
+            const u64 p = (u64)i0 + c;
+            key = (key << bits) | (p < n ? (u64)s_code[T[p]] + 1 : 0ull);
+        }
+        s_keys[IK_SLOT(l0)] = key;
+        for (u32 i = i0 + 1; i < iend; i++) {
+            const u64 p = (u64)i + k0 - 1;
+            key = ((key << bits) | (p < n ? (u64)s_code[T[p]] + 1 : 0ull)) & mask;
+            s_keys[IK_SLOT(l0 + (i - i0))] = key;
+        }
     }
-    keys[i0] = key;
-    for (u32 i = i0 + 1; i < iend; i++) {
-        const u64 p = (u64)i + k0 - 1;
-        key = ((key << bits) | (p < n ? (u64)s_code[T[p]] + 1 : 0ull)) & mask;
-        keys[i] = key;
-    }
+    init_keys_flush(s_keys, keys, blockIdx.x * 2048u, n);
 }
 
 // ---- key build of one doubling round ---------------------------------------------------------

@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) k_inv_spl_record(const u64 *__restrict__ 
 // Lanes are refilled: warp w owns the sublists [w Q, (w+1) Q) and a lane whose sublist ended takes
 // the next one of the warp's range (ballot + popc, no atomics), so the warp stays full until its
 // range runs dry.
-#define INV_SLOT_MAX 256  // staged bytes per sublist (`slot`): 4 x the mean sublist length, a multiple of 32, at most this
+#define INV_SLOT_MAX 512  // staged bytes per sublist (`slot`): 4 x the mean sublist length, a multiple of 32, at most this
 
 static __device__ __forceinline__ u32 byte_of_rank(const u32 *sC, u32 p)
 {

@@ -171,6 +171,18 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin_or_text, 
             if (vin) s_vals[p] = (p < cnt) ? vin[base + p] : 0u;
         }
     }
+    if (PACK) {
+        // the tile's text bytes, staged in the (otherwise unused) value area: s_txt[b] = T[base - 4 + b], so the byte
+        // before element p is s_txt[p + 3].  Whole words while they lie inside the text (base is a multiple of 4, the
+        // text pointer 16-byte aligned); the last tile goes byte by byte.
+        u8 *s_txt = (u8 *)s_vals;
+        if (bulk) {
+            const u32 *tw = (const u32 *)text + base / 4;
+            for (u32 w = tid; w <= (u32)TILE / 4; w += NT) s_vals[w] = (w == 0 && base == 0) ? 0u : ldg_stream_u32(tw + w - 1);
+        } else {
+            for (u32 p = tid; p < cnt; p += NT) s_txt[p + 3] = (base + p) ? text[base + p - 1] : (u8)0;
+        }
+    }
     __syncthreads();  // counters zeroed, barrier initialised (or the plain loads done)
     OS_PHASE(0);
     if (bulk) {
@@ -303,8 +315,8 @@ k_onesweep_pass(const K *__restrict__ kin, const u32 *__restrict__ vin_or_text, 
             const K k = s_keys[p];
             const u32 dst = s + s_adj[(u32)(k >> shift) & (RADIX_BINS - 1)];
             if (PACK) {
-                const u32 i = base + p;  // element index = text position; position 0 starts a factor (k_emit_heads)
-                const u32 byte = i ? (u32)text[i - 1] : 0u;
+                // element index base + p = text position; position 0 starts a factor (k_emit_heads)
+                const u32 byte = (u32)((const u8 *)s_vals)[p + 3];
                 vout[dst] = ((u32)k & ((1u << shift) - 1u)) | (byte << shift);
             } else {
                 kout[dst] = k;

@@ -335,6 +335,36 @@ def test_binned_rank_scatter_forced_on_small_inputs(bwts, ctx, oracle, gen):
         bwts.tune(7, 0)
 
 
+def test_initial_sort_histograms_from_window_counts(bwts, ctx, oracle, gen):
+    """the digit histograms of the initial sort come from one histogram of the leading symbols of the keys
+    (k_init_keys + k_digit_hists) for alphabets of 1-4, 6 and 8 bits per symbol, from k_radix_hist otherwise
+    (tune 21 = 1: always); every alphabet width, many short factors (the rotation wraps inside the key), narrow
+    keys (tune 6)"""
+    rng = np.random.default_rng(21)
+    cases = []
+    for sigma in (1, 2, 3, 4, 5, 8, 9, 16, 17, 32, 33, 64, 65, 128, 129, 256):
+        for n in (1, 5, 4097, 300_001):
+            cases.append((f"iid{sigma}", rng.integers(0, sigma, size=n, dtype=np.uint8).tobytes()))
+    cases.append(("descending", bytes(sorted(rng.integers(0, 256, size=200_000, dtype=np.uint8).tobytes(), reverse=True))))
+    cases.append(("descending4", bytes(sorted(rng.integers(97, 101, size=100_000, dtype=np.uint8).tobytes(), reverse=True))))
+    cases.append(("short factors", b"".join(bytes([255 - (i % 200)]) + b"ab" * (i % 7) for i in range(20_000))))
+    cases.append(("dna", gen.make("dna", 33, 3_000_000)))
+    cases.append(("text", gen.make("text", 34, 2_500_000)))
+    want = {name + str(len(x)): oracle.forward(x) for name, x in cases}
+    try:
+        for hist in (0, 1):
+            for keybits in (0, 40, 17):
+                bwts.tune(21, hist)
+                bwts.tune(6, keybits)
+                for name, x in cases:
+                    if keybits and len(x) > 400_000:
+                        continue
+                    assert ctx.forward_host(x) == want[name + str(len(x))], (name, len(x), hist, keybits)
+    finally:
+        bwts.tune(21, 0)
+        bwts.tune(6, 0)
+
+
 def test_binned_rank_scatter_in_later_rounds(bwts, ctx, oracle, gen):
     """re-ranks after the first one also send their ranks through the bin pass once a dense large-group set moves
     most of its ranks (tiled text: every rotation stays live for many rounds); tune 7 = 4 forces it for every

@@ -132,3 +132,30 @@ def test_onesweep_tile_permutation_is_the_stable_partition():
         digits = rng.integers(0, 256, size=tile)
         inv = model.onesweep_tile_permutation(digits)
         assert np.array_equal(inv, np.argsort(digits, kind="stable"))
+
+
+def test_digit_histograms_from_one_window_histogram():
+    """the eight digit histograms of the initial sort equal slices of one histogram of the leading symbols
+    (k_init_keys + k_digit_hists), for every alphabet width the driver uses it with, with short factors (the
+    rotation wraps many times inside the key) and narrow keys"""
+    rng = np.random.default_rng(12)
+    used = 0
+    for bits in (1, 2, 3, 4, 5, 6, 7, 8):
+        for k0 in sorted({max(1, 64 // bits), max(1, 40 // bits), 3, 1}):
+            if k0 * bits > 64:
+                continue
+            n = 600
+            codes = rng.integers(0, 1 << bits, size=n)
+            cuts = sorted(set(rng.integers(1, n, size=12).tolist()) | {1, 2, 5})   # factors of length 1, 1, 3, ...
+            starts = [0] + cuts + [n]
+            keys = model.initial_keys(codes, starts, bits, k0)
+            got = model.digit_hists_from_windows(keys, bits, k0)
+            if got is None:
+                assert bits in (5, 7) or k0 < 4, (bits, k0)
+                continue
+            used += 1
+            P0 = -(-(k0 * bits) // 8)
+            for p in range(P0):
+                want = np.bincount(np.array([(k >> (8 * p)) & 255 for k in keys]), minlength=256)
+                assert np.array_equal(got[p], want), (bits, k0, p)
+    assert used >= 12
