@@ -16,12 +16,12 @@ CLASS_OF = [
     (r"k_duval|k_chunkmin|k_chunk_threshold|k_sufmin|k_tile_min|k_prefix_min", "lyndon"),
     (r"k_flag_|k_set_u32|k_factor_lmax|k_coarse_index", "factor_table"),
     (r"k_byte_presence|k_code_table|k_init_keys", "init_keys"),
-    (r"k_radix_hist", "radix_hist"),
+    (r"k_radix_hist|k_digit_hists", "radix_hist"),
     (r"k_onesweep_pass<u64", "onesweep_pass"),
     (r"k_onesweep_pass<u32.*, 2>", "emit"),
     (r"k_onesweep_pass<u32", "rerank"),
     (r"k_build_keys", "build_keys"),
-    (r"k_rerank|k_bin_bases|k_scatter_pairs", "rerank"),
+    (r"k_rerank|k_bin_bases|k_bin_count|k_scatter_pairs", "rerank"),
     (r"k_emit|k_scatter_bytes|k_scatter_packed", "emit"),
     (r"k_local_sort|k_ls_probe", "local_sort"),
     (r"k_tuple|k_sample_lcp", "tuple_round"),
