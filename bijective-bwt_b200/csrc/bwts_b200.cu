@@ -540,22 +540,59 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     bool first = true, sortedL = true;  // the L set enters the loop freshly sorted (initial sort)
     bool binned_now = false;
     u64 changedL = 0;  // estimate of the ranks the last L re-rank moved
+    u64 changedS = ~0ull >> 4;  // the same for the S set; before its first re-rank: assume all of them
     bool sortedS = false;
     const LiveOut none = {nullptr, nullptr, nullptr, nullptr};
+    // rank[pos[j]] = nr[j] for j < m through one u32 onesweep pass that bins the pairs by the top 8 bits of the position
+    // and a streaming scatter, region by region (§4.2 "Where the ranks go")
+    auto scatter_binned = [&](const u32 *pos, const u32 *nr, u32 m, u32 *bin_pos, u32 *bin_val) -> int {
+        const u32 shift = kb - 8;
+        if (m == n) {
+            LAUNCH(KC_RERANK, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
+        } else {
+            CK(cudaMemsetAsync(sb.hist, 0, 256 * sizeof(u32), st));
+            LAUNCH(KC_RERANK, 4.0 * m, k_bin_count, min(cdiv(cdiv(m, 4), 256), 148u * 8u), 256, pos, m, shift, sb.hist);
+            LAUNCH(KC_RERANK, 0, k_radix_hist_scan, 1, 256, sb.hist);
+        }
+        do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
+        LaunchRec r__;
+        r__.cls = KC_RERANK; r__.bytes = 16.0 * m; r__.e0 = r__.e1 = nullptr; r__.name = "k_onesweep_pass<u32> bin";
+        if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
+        k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(m, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
+            pos, nr, bin_pos, bin_val, m, shift, sb.hist, sb.status, ctx->epoch);
+        if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
+        r__.phase = ctx->phase; ctx->recs.push_back(r__);
+        CK(cudaGetLastError());
+        LAUNCH(KC_RERANK, 12.0 * m, k_scatter_pairs, cdiv(cdiv(m, 8), 256), 256, bin_pos, bin_val, m, rank);
+        ctx->stats.binned_rounds++;
+        return 0;
+    };
     for (;;) {
         // ---- re-rank what was just sorted; S first, L appends to the same S stream
         ctx->phase = PH_ISA;
         CK(cudaMemsetAsync(rrc, 0, 2 * sizeof(RerankCounters), st));
         const LiveOut oS = {vS, grpS, gstS, nullptr};  // in place
+        // The S set's ranks take the binned route as well while a third of them move per round (text: the first
+        // small-group round resolves nearly every tie; C5 block 37.1 -> 35.7 ms).
+        // Its idx array is compacted in place, so the kernel copies the positions out next to the ranks: three streams
+        // of mS words in the idle key buffer (8n bytes), the binned ranks in kS once the kernel has read its keys.
+        const bool binS = mS && sortedS && use_binned_scatter(n, kb) && g_tune_scatterbin != 3 && 3ull * mS + 16 <= 2ull * n &&
+                          (g_tune_scatterbin == 4 || (n >= (1u << 27) && mS >= (1u << 20) && 3ull * changedS >= mS));
+        const size_t mS4 = ((size_t)mS + 3) & ~(size_t)3;
+        u32 *nrS = binS ? (u32 *)sb.k[sb.cur ^ 1] : (u32 *)nullptr, *posS = binS ? nrS + mS4 : (u32 *)nullptr;
         if (mS && sortedS) {
             CK(cudaMemsetAsync(rr_statusA, 0, rr_status_bytes(mS), st));
             CK(cudaMemsetAsync(rr_statusB, 0, rr_status_bytes(mS), st));
             if (t_on) {
                 LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<2, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
-                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, nxtT[tc], tmax, thead);
+                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, nrS, posS, nxtT[tc], tmax, thead);
             } else {
                 LAUNCH(KC_RERANK, 20.0 * mS, (k_rerank<0, u32>), cdiv(mS, RR_TILE), RR_NT, kS, vS, grpS, gstS, mS, 0, rank, oS,
-                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
+                       (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc + 0, nrS, posS, (u32 *)nullptr, 0u, 0u);
+            }
+            if (binS) {
+                rc = scatter_binned(posS, nrS, mS, posS + mS4, kS);
+                if (rc) return rc;
             }
         }
         if (mL && sortedL) {
@@ -567,47 +604,32 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             // 85 B moved per element).  Instead the ranks go out in sorted order, one u32 onesweep
             // pass bins the (position, rank) pairs by the top 8 bits of the position, and a
             // streaming kernel scatters them region by region through L2.
-            // Later rounds of repetitive inputs (tiled text: every rotation stays live for 18 rounds) do the same
-            // once most ranks move again: at least half of the positions live and a third of the ranks changed in
-            // the round before.  Sparse sets gain nothing (one store per DRAM atom either way).
+            // Later re-ranks do the same when a third of the set's ranks moved in the round before (k_rerank counts
+            // them): the streams cost ~20 ps per slot, a directly scattered rank 36-50 ps.  The density of the set
+            // does not matter -- the DRAM bytes per moved rank are the same either way, what the regions buy is
+            // page and TLB locality (C4, sets of 15-18 % of the positions: forward 267.9 -> 259.0 ms).  From 128 Mi
+            // bytes on: at 64 MiB (rank[] = twice the L2) the direct scatter is level or ahead (C2 8.30 against 8.39 ms).
             const bool binned = use_binned_scatter(n, kb) &&
                                 (first || g_tune_scatterbin == 4 ||
-                                 (g_tune_scatterbin != 3 && 2ull * mL >= n && 3ull * changedL >= mL));
+                                 (g_tune_scatterbin != 3 && n >= (1u << 27) && mL >= (1u << 20) && 3ull * changedL >= mL));
             binned_now = binned;
             u32 *nr_out = binned ? (u32 *)sb.k[sb.cur ^ 1] : (u32 *)nullptr;  // the idle key buffer: 8n bytes
             if (g_tune_local) {
                 LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<0, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oL, (const u32 *)nullptr, none,
-                       rr_statusA, rr_statusB, rrc + 1, nr_out, (u32 *)nullptr, 0u, 0u);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out, (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
             } else {
                 LAUNCH(KC_RERANK, 24.0 * mL, (k_rerank<1, u64>), cdiv(mL, RR_TILE), RR_NT, sb.k[sb.cur], sb.v[sb.cur],
                        first ? (const u32 *)nullptr : grp, gst, mL, 0, rank, oS, (const u32 *)&rrc[0].keptS, oL,
-                       rr_statusA, rr_statusB, rrc + 1, nr_out, t_on ? nxtT[tc] : (u32 *)nullptr, t_on ? tmax : 0u, thead);
+                       rr_statusA, rr_statusB, rrc + 1, nr_out, (u32 *)nullptr, t_on ? nxtT[tc] : (u32 *)nullptr, t_on ? tmax : 0u, thead);
             }
         }
         if (mL && sortedL && binned_now) {
             // scratch: rank stream + binned positions in the idle key buffer, binned ranks in kS (the key2 array of the S
             // set is dead between its re-rank above and the warp-local sort of the coming round, which writes it)
             u32 *nr_buf = (u32 *)sb.k[sb.cur ^ 1], *bin_pos = nr_buf + (((size_t)n + 3) & ~(size_t)3), *bin_val = kS;
-            const u32 shift = kb - 8;
-            if (mL == n) {
-                LAUNCH(KC_RERANK, 0, k_bin_bases, 1, 256, n, shift, sb.hist);
-            } else {
-                CK(cudaMemsetAsync(sb.hist, 0, 256 * sizeof(u32), st));
-                LAUNCH(KC_RERANK, 4.0 * mL, k_bin_count, min(cdiv(cdiv(mL, 4), 256), 148u * 8u), 256, sb.v[sb.cur], mL, shift, sb.hist);
-                LAUNCH(KC_RERANK, 0, k_radix_hist_scan, 1, 256, sb.hist);
-            }
-            do { ctx->epoch = (g_epoch.fetch_add(1) + 1) & 0x3fffffffu; } while (ctx->epoch == 0);
-            LaunchRec r__;
-            r__.cls = KC_RERANK; r__.bytes = 16.0 * mL; r__.e0 = r__.e1 = nullptr; r__.name = "k_onesweep_pass<u32> bin";
-            if (ctx->profile) { r__.e0 = ctx_event(ctx); if (r__.e0) cudaEventRecord(r__.e0, st); }
-            k_onesweep_pass<u32, 384, 12, 3, 4><<<cdiv(mL, 384 * 12), 384, OsSmem<u32, 384, 12>::bytes, st>>>(
-                sb.v[sb.cur], nr_buf, bin_pos, bin_val, mL, shift, sb.hist, sb.status, ctx->epoch);
-            if (ctx->profile && r__.e0) { r__.e1 = ctx_event(ctx); if (r__.e1) cudaEventRecord(r__.e1, st); }
-            r__.phase = ctx->phase; ctx->recs.push_back(r__);
-            CK(cudaGetLastError());
-            LAUNCH(KC_RERANK, 12.0 * mL, k_scatter_pairs, cdiv(cdiv(mL, 8), 256), 256, bin_pos, bin_val, mL, rank);
-            ctx->stats.binned_rounds++;
+            rc = scatter_binned(sb.v[sb.cur], nr_buf, mL, bin_pos, bin_val);
+            if (rc) return rc;
         }
         rc = readback(ctx, st, rrc, 2 * sizeof(RerankCounters) + 16);
         if (rc) return rc;
@@ -617,6 +639,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         const u32 *tc_h = (const u32 *)((const RerankCounters *)ctx->h_small + 2);
         const bool splitT = tc_h[1] != 0;
         changedL = 16ull * ((u64)cL.changed[0] + cL.changed[1] + cL.changed[2] + cL.changed[3]);
+        if (mS && sortedS) changedS = 16ull * ((u64)cS.changed[0] + cS.changed[1] + cS.changed[2] + cS.changed[3]);
         u32 headsS = 0, headsL = 0, kheadsS = 0, kheadsL_all = 0, enteredT = 0;
         for (int q = 0; q < RR_SPREAD; q++) {
             headsS += cS.heads[q]; headsL += cL.heads[q];
@@ -657,7 +680,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                 CK(cudaMemsetAsync(rrc, 0, sizeof(RerankCounters), st));
                 LAUNCH(KC_RERANK, 16.0 * mS, (k_rerank<0, u32>), cdiv(mS, RR_TILE), RR_NT, (const u32 *)nullptr, vS,
                        grpS, gstS, mS, 1, rank, none, (const u32 *)nullptr, none, rr_statusA, rr_statusB, rrc,
-                       (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
+                       (u32 *)nullptr, (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
             }
             if (mL) {
                 CK(cudaMemsetAsync(rr_statusA, 0, rr_status_bytes(mL), st));
@@ -665,7 +688,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
                 CK(cudaMemsetAsync(rrc + 1, 0, sizeof(RerankCounters), st));
                 LAUNCH(KC_RERANK, 16.0 * mL, (k_rerank<0, u64>), cdiv(mL, RR_TILE), RR_NT, (const u64 *)nullptr,
                        sb.v[sb.cur], grp, gst, mL, 1, rank, none, (const u32 *)nullptr, none, rr_statusA,
-                       rr_statusB, rrc + 1, (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
+                       rr_statusB, rrc + 1, (u32 *)nullptr, (u32 *)nullptr, (u32 *)nullptr, 0u, 0u);
             }
             if (mT) {  // members of a final tie take consecutive slots in text order, the rings dissolve
                 CK(cudaMemsetAsync(tcnt, 0, 16, st));

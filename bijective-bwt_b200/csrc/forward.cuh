@@ -286,7 +286,8 @@ struct LiveOut {  // one compaction stream
 // baseS: device word holding the number of elements already in the S stream (nullptr = 0).
 // nr_out != nullptr: the new rank of slot j is stored at nr_out[j] instead of being scattered to
 // rank[idx[j]]; the caller bins the (idx, rank) pairs by text region and scatters them with
-// locality (first re-rank of large inputs, where every one of the n ranks is written).
+// locality (first re-rank of large inputs, where every one of the n ranks is written; later re-ranks of
+// dense sets).  pos_out != nullptr: idx[j] is copied to pos_out[j] as well (sets compacted in place).
 //
 // IN PLACE: outS / outL may alias the input arrays (idx, grp, gst).  A tile writes its kept
 // elements at [exclusive prefix, +kept), which never lies beyond its own input region, and it
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(RR_NT, RR_MINB) k_rerank(const KeyT *__restric
                                                   const u32 *__restrict__ baseS, LiveOut outL,
                                                   u64 *__restrict__ statusA, u64 *__restrict__ statusB,
                                                   RerankCounters *__restrict__ ctr, u32 *__restrict__ nr_out,
-                                                  u32 *__restrict__ nxtT, u32 tmax, u32 head_flag)
+                                                  u32 *__restrict__ pos_out, u32 *__restrict__ nxtT, u32 tmax, u32 head_flag)
 {
     // compaction staging (outputs phase) -- and, before the look-back, st_idx doubles as `s_all`: idx by tile
     // slot for the ring links of the tuple set (every thread is past the routing when the staging starts:
@@ -648,6 +649,16 @@ __global__ void __launch_bounds__(RR_NT, RR_MINB) k_rerank(const KeyT *__restric
 #pragma unroll
             for (int q = 0; q < RR_IPT; q++)
                 if ((u32)q < mine) nr_out[j0 + q] = nrv[q];
+        }
+    }
+    if (pos_out) {  // the S set compacts idx in place: the bin pass needs its own copy of the positions
+        if (full) {
+            ((uint4 *)(pos_out + j0))[0] = make_uint4(vi[0], vi[1], vi[2], vi[3]);
+            ((uint4 *)(pos_out + j0))[1] = make_uint4(vi[4], vi[5], vi[6], vi[7]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < RR_IPT; q++)
+                if ((u32)q < mine) pos_out[j0 + q] = vi[q];
         }
     }
     PH(22);  // ranks + staging

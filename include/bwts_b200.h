@@ -146,8 +146,9 @@ const char *bwts_b200_version(void);
  * warp-local sort path (1), 4 = force the suffix-sort fallback for the Lyndon boundaries (1),
  * 5 = no copy/compute overlap between the blocks of one device (1), 6 = cap on the bits of
  * the initial packed key (8..64), 7 = binned rank scatter of the re-ranks (1 = never, 2 = the first
- * re-rank of inputs of any size, 3 = the first re-rank only, 4 = every re-rank of the large-group set; default:
- * inputs of 4 Mi bytes and more, the first re-rank and later ones that move the ranks of a dense set), 8 = never sort the large-group set
+ * re-rank of inputs of any size, 3 = the first re-rank only, 4 = every re-rank of both rank-ordered sets; default:
+ * the first re-rank of inputs of 4 Mi bytes and more, later ones from 128 Mi bytes on when a third of the set's
+ * ranks moved in the round before), 8 = never sort the large-group set
  * CTA-locally (1), 9 = emit through rank windows (1), binned by rank region as one packed word per
  * element (2; default from 512 Mi bytes) or as (rank, byte) pairs in two streams (3), 10 = cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured: no
  * effect), 12 = inverse through two read-only walks (1) instead of the staged single walk, 13 =
