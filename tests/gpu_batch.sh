@@ -5,5 +5,4 @@ N=${1:-2}
 out=gpurun_out/r3c_n$N; mkdir -p $out
 nvidia-smi topo -m > $out/topo.txt 2>&1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 > $out/bench_c5_n$N.json 2> $out/bench_c5_n$N.err; echo "bench rc=$?" >> $out/bench_c5_n$N.err
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "dealer or devices or blocks" > $out/pytest.txt 2>&1; echo "pytest rc=$?" >> $out/pytest.txt
-tail -n 3 $out/pytest.txt; tail -n 2 $out/bench_c5_n$N.err; grep -c '^{' $out/bench_c5_n$N.json
+tail -n 2 $out/bench_c5_n$N.err; grep -c '^{' $out/bench_c5_n$N.json
