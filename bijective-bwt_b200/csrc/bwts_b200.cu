@@ -47,6 +47,7 @@ static long g_tune_nocta = 0;      // 1 = never use the CTA-local sort for the L
 static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter when n >= 4 Mi, 1 = never, 2 = always
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
 static long g_tune_hist = 0;       // 1 = digit histograms of the initial sort by k_radix_hist (eight shared atomics per key)
+static long g_tune_partial = 0;    // 1 = initial keys of whole symbols only (no partial symbol in the spare bits)
 static long g_tune_ctasort = 0;    // CTA-local sort: 0 = radix in shared memory, 1 = bitonic network (round 1)
 static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = Hillis-Steele levels under a probe budget, else CTA-wide; 1 / 2 = force either
 static long g_tune_tmode = 0;      // tuple set: 0 = one thread per member (up to 8 members), 1 = one thread per group (up to 32)
@@ -486,27 +487,33 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     const u32 bits = max(1, bit_length(syms - 1));
     const u32 keybits = (g_tune_keybits >= 8 && g_tune_keybits <= 64) ? (u32)g_tune_keybits : 64u;
     const u32 k0 = max(1u, keybits / bits);
-    const int P0 = (int)cdiv((u64)k0 * bits, 8);
+    // bits the whole symbols leave free take the top of the next symbol (k_init_keys; tune 22 = 1: off)
+    const u32 extra = (linear || g_tune_partial == 1 || keybits <= k0 * bits) ? 0u : min(bits - 1, keybits - k0 * bits);
+    const int P0 = (int)cdiv((u64)k0 * bits + extra, 8);
     ctx->stats.alphabet_bits = (int)bits;
     ctx->stats.initial_depth = (int)k0;
 
     // digit histograms of the initial sort from one histogram of the leading symbols (k_init_keys): possible when the
     // widest digit spans symbols worth at most 12 bits (alphabets of 1-4, 6 and 8 bits per symbol)
     u32 wsyms = 0;
-    for (int p = 0; p < P0; p++) {
-        const u32 lo_bit = 8u * p, hi_bit = min(8u * p + 7u, k0 * bits - 1u);
-        wsyms = max(wsyms, hi_bit / bits - lo_bit / bits + 1u);
+    {
+        const u32 k0p = k0 + (extra ? 1u : 0u), d = extra ? bits - extra : 0u;
+        for (int p = 0; p < P0; p++) {
+            const u32 lo_bit = 8u * p + d, hi_bit = min(8u * p + 7u + d, k0p * bits - 1u);
+            wsyms = max(wsyms, hi_bit / bits - lo_bit / bits + 1u);
+        }
     }
     const bool use_wh = !linear && g_tune_hist != 1 && wsyms * bits <= 12 && k0 >= wsyms;
     const u32 wbins = use_wh ? 1u << (wsyms * bits) : 0u;
     if (!linear) {
         if (use_wh) CK(cudaMemsetAsync(whist, 0, wbins * sizeof(u32), st));
         LAUNCH_SMEM(KC_INIT_KEYS, 9.0 * n, k_init_keys, min(cdiv(n, 2048), (u32)ctx->sm_count * 6u), 256, wbins * sizeof(u32), dT, n,
-                    FS, cidx, code, bits, k0, sb.k[0], use_wh ? whist : (u32 *)nullptr, bits * (k0 - min(k0, wsyms)), wbins);
+                    FS, cidx, code, bits, k0, extra, sb.k[0], use_wh ? whist : (u32 *)nullptr,
+                    extra + bits * (k0 - min(k0, wsyms)), wbins);
     } else {
         LAUNCH(KC_INIT_KEYS, 9.0 * n, k_init_keys_linear, cdiv(cdiv(n, 8), 256), 256, dT, n, code, bits, k0, sb.k[0]);
     }
-    if (use_wh) LAUNCH(KC_RADIX_HIST, 4.0 * wbins * P0, k_digit_hists, P0, 256, whist, wbins, wsyms, bits, k0, sb.hist);
+    if (use_wh) LAUNCH(KC_RADIX_HIST, 4.0 * wbins * P0, k_digit_hists, P0, 256, whist, wbins, wsyms, bits, k0, extra, sb.hist);
     rc = radix_sort(ctx, st, sb, n, P0, true, use_wh);
     if (rc) return rc;
 
@@ -1714,6 +1721,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 18) { g_tune_ctasort = value; return 0; }
     if (key == 20) { g_tune_tmode = value; return 0; }
     if (key == 21) { g_tune_hist = value; return 0; }
+    if (key == 22) { g_tune_partial = value; return 0; }
     if (key == 16) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invbudget = value; return 0; }
     if (key == 13) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invq = value; return 0; }
     return BWTS_B200_EINVAL;

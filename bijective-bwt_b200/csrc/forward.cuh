@@ -70,10 +70,14 @@ static __device__ __forceinline__ void init_keys_flush(const u64 *s_keys, u64 *_
 // So ONE histogram of the leading w symbols (`whist`, 2^(w * bits) <= 4096 bins, one shared atomic per key, taken here
 // while the key is in a register) holds all eight digit histograms; k_digit_hists reads them off.
 // Grid-stride over tiles of 2048 positions: the window histogram is flushed once per CTA.
+// `extra` > 0: the bits the k0 whole symbols leave free in the 64-bit key (4 of them for 6-bit alphabets) hold the top
+// bits of symbol k0 + 1.  Ranks that are finer than "order by k0 symbols" but still consistent with the order of the
+// rotations are as good for the doubling as the exact ones (a round only needs ties to mean "equal on at least k
+// symbols"), and on text a third of the ties of the initial sort end there: fewer rotations enter the doubling rounds.
 __global__ void __launch_bounds__(256) k_init_keys(const u8 *__restrict__ T, u32 n, const u32 *__restrict__ FS,
                                                    const u32 *__restrict__ cidx, const u8 *__restrict__ code,
-                                                   u32 bits, u32 k0, u64 *__restrict__ keys, u32 *__restrict__ whist,
-                                                   u32 wshift, u32 wbins)
+                                                   u32 bits, u32 k0, u32 extra, u64 *__restrict__ keys,
+                                                   u32 *__restrict__ whist, u32 wshift, u32 wbins)
 {
     extern __shared__ u32 s_wh[];  // wbins words when whist != nullptr
     __shared__ u8 s_code[256];
@@ -84,6 +88,8 @@ __global__ void __launch_bounds__(256) k_init_keys(const u8 *__restrict__ T, u32
     __syncthreads();
     const u32 l0 = threadIdx.x * 8;
     const u64 mask = (k0 * bits >= 64) ? ~0ull : ((1ull << (k0 * bits)) - 1);
+    const u32 look = k0 + (extra ? 1u : 0u);  // symbols a key reads
+    const u32 pshift = bits - extra;          // the partial symbol keeps its top `extra` bits
     const u32 ntiles = (n + 2047u) / 2048u;
     for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const u32 i0 = tile * 2048u + l0;
@@ -99,14 +105,23 @@ __global__ void __launch_bounds__(256) k_init_keys(const u8 *__restrict__ T, u32
                 key = (key << bits) | s_code[T[pos]];
                 pos = (pos + 1 == e) ? s : pos + 1;
             }
-            s_keys[IK_SLOT(l0 + (i - i0))] = key;
-            if (whist) atomicAdd(&s_wh[(u32)(key >> wshift)], 1u);
+            u32 nextc = extra ? (u32)s_code[T[pos]] : 0u;  // symbol k0 + 1 of this rotation
+            u64 full = extra ? ((key << extra) | (u64)(nextc >> pshift)) : key;
+            s_keys[IK_SLOT(l0 + (i - i0))] = full;
+            if (whist) atomicAdd(&s_wh[(u32)(full >> wshift)], 1u);
             i++;
-            // slide while the window [i, i+k0) stays inside the factor
-            while (i < iend && i < e && (u64)i + k0 <= e) {
-                key = ((key << bits) | s_code[T[i + k0 - 1]]) & mask;
-                s_keys[IK_SLOT(l0 + (i - i0))] = key;
-                if (whist) atomicAdd(&s_wh[(u32)(key >> wshift)], 1u);
+            // slide while the window [i, i + look) stays inside the factor
+            while (i < iend && i < e && (u64)i + look <= e) {
+                if (extra) {
+                    key = ((key << bits) | nextc) & mask;
+                    nextc = s_code[T[i + k0]];
+                    full = (key << extra) | (u64)(nextc >> pshift);
+                } else {
+                    key = ((key << bits) | s_code[T[i + k0 - 1]]) & mask;
+                    full = key;
+                }
+                s_keys[IK_SLOT(l0 + (i - i0))] = full;
+                if (whist) atomicAdd(&s_wh[(u32)(full >> wshift)], 1u);
                 i++;
             }
         }
@@ -120,22 +135,24 @@ __global__ void __launch_bounds__(256) k_init_keys(const u8 *__restrict__ T, u32
         }
     }
 }
-// ghist[p][d] = sum of whist[W] over the windows W whose slice for digit p is d.  Digit p = key bits [8p, 8p + 8);
-// symbol t of the key sits at bits [bits * (k0-1-t), bits * (k0-t)).  With t_lo / t_hi the symbols holding the lowest
-// / highest key bit of the digit (clipped to the key width), the digit is a slice of the first t_lo - t_hi + 1 symbols
-// of the window.  One block per digit.
+// ghist[p][d] = sum of whist[W] over the windows W whose slice for digit p is d.  Digit p = key bits [8p, 8p + 8).
+// The key is the packing K of k0' = k0 (+ 1 with a partial symbol) symbols, symbol t at K bits [bits * (k0'-1-t),
+// bits * (k0'-t)), shifted right by d = bits - extra (0 without a partial symbol): key bit b = K bit b + d.  With
+// t_lo / t_hi the symbols holding the lowest / highest K bit of the digit (clipped to the key width), the digit is a
+// slice of the first t_lo - t_hi + 1 symbols of the window that starts t_hi symbols into the rotation.  One block per digit.
 __global__ void __launch_bounds__(256) k_digit_hists(const u32 *__restrict__ whist, u32 wbins, u32 wsyms, u32 bits, u32 k0,
-                                                     u32 *__restrict__ ghist)
+                                                     u32 extra, u32 *__restrict__ ghist)
 {
     __shared__ u32 sh[256];
     const u32 p = blockIdx.x;
     sh[threadIdx.x] = 0;
     __syncthreads();
-    const u32 lo_bit = 8 * p, hi_bit = min(8 * p + 7, k0 * bits - 1);
-    const u32 t_lo = k0 - 1 - lo_bit / bits, t_hi = k0 - 1 - hi_bit / bits;
-    const u32 wp = t_lo - t_hi + 1;                   // symbols the digit touches (<= wsyms)
-    const u32 drop = bits * (wsyms - wp);             // trailing symbols of the window the digit does not see
-    const u32 sh_r = lo_bit - bits * (k0 - 1 - t_lo);  // digit's lowest bit inside symbol t_lo
+    const u32 k0p = k0 + (extra ? 1u : 0u), d = extra ? bits - extra : 0u;
+    const u32 lo_bit = 8 * p + d, hi_bit = min(8 * p + 7 + d, k0p * bits - 1);
+    const u32 t_lo = k0p - 1 - lo_bit / bits, t_hi = k0p - 1 - hi_bit / bits;
+    const u32 wp = t_lo - t_hi + 1;                    // symbols the digit touches (<= wsyms)
+    const u32 drop = bits * (wsyms - wp);              // trailing symbols of the window the digit does not see
+    const u32 sh_r = lo_bit - bits * (k0p - 1 - t_lo);  // digit's lowest bit inside symbol t_lo
     for (u32 w = threadIdx.x; w < wbins; w += 256) {
         const u32 c = whist[w];
         if (c) atomicAdd(&sh[((w >> drop) >> sh_r) & 255u], c);

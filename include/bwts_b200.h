@@ -159,7 +159,8 @@ const char *bwts_b200_version(void);
  * chosen by the match lengths of the first level), 18 = CTA-local sort as the bitonic network of
  * round 1 (1) instead of the radix sort in shared memory, 20 = tuple set with one thread per group and
  * groups of up to 32 (1; measured slower than one thread per member), 21 = digit histograms of the initial sort by a
- * sweep over the keys (1) instead of the window histogram taken while the keys are built.  value 0 = default. */
+ * sweep over the keys (1) instead of the window histogram taken while the keys are built, 22 = initial keys of whole
+ * symbols only (1; default: spare key bits hold the top bits of the next symbol).  value 0 = default. */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */

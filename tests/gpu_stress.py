@@ -61,7 +61,7 @@ with bwts.Context(0) as ctx:
         knobs = {7: int(rng.choice([0, 0, 1, 2, 4, 4])), 8: int(rng.random() < 0.2), 9: int(rng.choice([0, 1, 2, 3])),
                  12: int(rng.random() < 0.2), 14: int(rng.choice([0, 1, 2, 3, 8, 32])), 15: int(rng.choice([0, 1, 2])),
                  17: int(rng.choice([0, 1, 2])), 18: int(rng.random() < 0.3), 20: int(rng.random() < 0.4),
-                 21: int(rng.random() < 0.3), 6: int(rng.choice([0, 0, 0, 24, 40, 56]))}
+                 21: int(rng.random() < 0.3), 22: int(rng.random() < 0.3), 6: int(rng.choice([0, 0, 0, 24, 40, 56]))}
         for key, val in knobs.items():
             bwts.tune(key, val)
         wf, wi = oracle.forward(x), oracle.inverse(x)

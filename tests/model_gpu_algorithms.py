@@ -573,9 +573,9 @@ def onesweep_tile_permutation(digits):
     return inv
 
 
-def initial_keys(codes, starts, bits, k0):
-    """k_init_keys: key[i] = the first k0 symbols (codes, `bits` each) of the rotation of i's factor starting at i;
-    `starts` = factor starts + [n]"""
+def initial_keys(codes, starts, bits, k0, extra=0):
+    """k_init_keys: key[i] = the first k0 symbols (codes, `bits` each) of the rotation of i's factor starting at i,
+    followed by the top `extra` bits of symbol k0 + 1 (extra < bits); `starts` = factor starts + [n]"""
     n = len(codes)
     keys = [0] * n
     for f in range(len(starts) - 1):
@@ -585,31 +585,34 @@ def initial_keys(codes, starts, bits, k0):
             k = 0
             for t in range(k0):
                 k = (k << bits) | int(codes[s + (i - s + t) % L])
+            if extra:
+                k = (k << extra) | (int(codes[s + (i - s + k0) % L]) >> (bits - extra))
             keys[i] = k
     return keys
 
 
-def digit_hists_from_windows(keys, bits, k0):
+def digit_hists_from_windows(keys, bits, k0, extra=0):
     """k_init_keys' window histogram + k_digit_hists: the 256-bin histogram of every radix digit of the keys, read
     off ONE histogram of the leading `wsyms` symbols.  Returns None where the driver keeps k_radix_hist
     (windows wider than 12 bits)."""
-    P0 = -(-(k0 * bits) // 8)
+    k0p, d = k0 + (1 if extra else 0), (bits - extra) if extra else 0
+    P0 = -(-(k0 * bits + extra) // 8)
     span = []
     for p in range(P0):
-        lo_bit, hi_bit = 8 * p, min(8 * p + 7, k0 * bits - 1)
+        lo_bit, hi_bit = 8 * p + d, min(8 * p + 7 + d, k0p * bits - 1)
         span.append(hi_bit // bits - lo_bit // bits + 1)
     wsyms = max(span)
     if wsyms * bits > 12 or k0 < wsyms:
         return None
-    wshift = bits * (k0 - wsyms)
+    wshift = extra + bits * (k0 - wsyms)
     whist = np.bincount(np.array([k >> wshift for k in keys], dtype=np.int64), minlength=1 << (wsyms * bits))
     out = np.zeros((P0, 256), dtype=np.int64)
     for p in range(P0):
-        lo_bit, hi_bit = 8 * p, min(8 * p + 7, k0 * bits - 1)
-        t_lo, t_hi = k0 - 1 - lo_bit // bits, k0 - 1 - hi_bit // bits
+        lo_bit, hi_bit = 8 * p + d, min(8 * p + 7 + d, k0p * bits - 1)
+        t_lo, t_hi = k0p - 1 - lo_bit // bits, k0p - 1 - hi_bit // bits
         wp = t_lo - t_hi + 1
         drop = bits * (wsyms - wp)
-        sh_r = lo_bit - bits * (k0 - 1 - t_lo)
+        sh_r = lo_bit - bits * (k0p - 1 - t_lo)
         for w in np.flatnonzero(whist):
             out[p][((int(w) >> drop) >> sh_r) & 255] += whist[w]
     return out

@@ -339,7 +339,8 @@ def test_binned_rank_scatter_forced_on_small_inputs(bwts, ctx, oracle, gen):
 def test_initial_sort_histograms_from_window_counts(bwts, ctx, oracle, gen):
     """the digit histograms of the initial sort come from one histogram of the leading symbols of the keys
     (k_init_keys + k_digit_hists) for alphabets of 1-4, 6 and 8 bits per symbol, from k_radix_hist otherwise
-    (tune 21 = 1: always); every alphabet width, many short factors (the rotation wraps inside the key), narrow
+    (tune 21 = 1: always); the bits the whole symbols leave free in the key hold the top of one more symbol
+    (tune 22 = 1: off); every alphabet width, many short factors (the rotation wraps inside the key), narrow
     keys (tune 6)"""
     rng = np.random.default_rng(21)
     cases = []
@@ -353,16 +354,18 @@ def test_initial_sort_histograms_from_window_counts(bwts, ctx, oracle, gen):
     cases.append(("text", gen.make("text", 34, 2_500_000)))
     want = {name + str(len(x)): oracle.forward(x) for name, x in cases}
     try:
-        for hist in (0, 1):
+        for hist, partial in ((0, 0), (1, 0), (0, 1), (1, 1)):
             for keybits in (0, 40, 17):
                 bwts.tune(21, hist)
+                bwts.tune(22, partial)
                 bwts.tune(6, keybits)
                 for name, x in cases:
-                    if keybits and len(x) > 400_000:
+                    if (keybits or partial) and len(x) > 400_000:
                         continue
-                    assert ctx.forward_host(x) == want[name + str(len(x))], (name, len(x), hist, keybits)
+                    assert ctx.forward_host(x) == want[name + str(len(x))], (name, len(x), hist, partial, keybits)
     finally:
         bwts.tune(21, 0)
+        bwts.tune(22, 0)
         bwts.tune(6, 0)
 
 

@@ -137,25 +137,47 @@ def test_onesweep_tile_permutation_is_the_stable_partition():
 def test_digit_histograms_from_one_window_histogram():
     """the eight digit histograms of the initial sort equal slices of one histogram of the leading symbols
     (k_init_keys + k_digit_hists), for every alphabet width the driver uses it with, with short factors (the
-    rotation wraps many times inside the key) and narrow keys"""
+    rotation wraps many times inside the key), narrow keys, and keys whose spare bits hold the top of one more symbol"""
     rng = np.random.default_rng(12)
-    used = 0
+    used = used_extra = 0
     for bits in (1, 2, 3, 4, 5, 6, 7, 8):
-        for k0 in sorted({max(1, 64 // bits), max(1, 40 // bits), 3, 1}):
+        for keybits in (64, 40, 24, 9):
+            k0 = max(1, keybits // bits)
             if k0 * bits > 64:
                 continue
-            n = 600
-            codes = rng.integers(0, 1 << bits, size=n)
-            cuts = sorted(set(rng.integers(1, n, size=12).tolist()) | {1, 2, 5})   # factors of length 1, 1, 3, ...
-            starts = [0] + cuts + [n]
-            keys = model.initial_keys(codes, starts, bits, k0)
-            got = model.digit_hists_from_windows(keys, bits, k0)
-            if got is None:
-                assert bits in (5, 7) or k0 < 4, (bits, k0)
-                continue
-            used += 1
-            P0 = -(-(k0 * bits) // 8)
-            for p in range(P0):
-                want = np.bincount(np.array([(k >> (8 * p)) & 255 for k in keys]), minlength=256)
-                assert np.array_equal(got[p], want), (bits, k0, p)
-    assert used >= 12
+            for extra in sorted({0, min(bits - 1, max(0, keybits - k0 * bits))}):
+                n = 600
+                codes = rng.integers(0, 1 << bits, size=n)
+                cuts = sorted(set(rng.integers(1, n, size=12).tolist()) | {1, 2, 5})   # factors of length 1, 1, 3, ...
+                starts = [0] + cuts + [n]
+                keys = model.initial_keys(codes, starts, bits, k0, extra)
+                assert max(keys) < 1 << (k0 * bits + extra)
+                got = model.digit_hists_from_windows(keys, bits, k0, extra)
+                if got is None:
+                    continue
+                used += 1
+                used_extra += extra > 0
+                P0 = -(-(k0 * bits + extra) // 8)
+                for p in range(P0):
+                    want = np.bincount(np.array([(k >> (8 * p)) & 255 for k in keys]), minlength=256)
+                    assert np.array_equal(got[p], want), (bits, k0, extra, p)
+    assert used >= 16 and used_extra >= 3, (used, used_extra)
+
+
+def test_partial_symbol_keys_refine_the_order_consistently():
+    """keys with the top bits of symbol k0 + 1 in their spare bits order the rotations consistently with the
+    omega-order and tie only where the first k0 symbols are equal: what the doubling rounds need of the initial ranks"""
+    rng = np.random.default_rng(13)
+    for bits, k0, extra in ((6, 10, 4), (6, 3, 4), (7, 9, 1), (5, 12, 4), (3, 5, 1)):
+        n = 300
+        codes = rng.integers(0, min(1 << bits, 5), size=n)
+        starts = [0, 7, 8, 120, n]
+        plain = model.initial_keys(codes, starts, bits, k0, 0)
+        fine = model.initial_keys(codes, starts, bits, k0, extra)
+        deep = model.initial_keys(codes, starts, bits, k0 + 1, 0)   # one whole symbol more
+        for a in range(0, n, 7):
+            for b in range(n):
+                if fine[a] == fine[b]:
+                    assert plain[a] == plain[b]
+                if fine[a] < fine[b]:
+                    assert deep[a] <= deep[b] and plain[a] <= plain[b]
