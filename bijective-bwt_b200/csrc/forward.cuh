@@ -303,8 +303,8 @@ struct LiveOut {  // one compaction stream
 // baseS: device word holding the number of elements already in the S stream (nullptr = 0).
 // nr_out != nullptr: the new rank of slot j is stored at nr_out[j] instead of being scattered to
 // rank[idx[j]]; the caller bins the (idx, rank) pairs by text region and scatters them with
-// locality (first re-rank of large inputs, where every one of the n ranks is written; later re-ranks of
-// dense sets).  pos_out != nullptr: idx[j] is copied to pos_out[j] as well (sets compacted in place).
+// locality (first re-rank of large inputs, where every one of the n ranks is written; later re-ranks that
+// move a third of their set's ranks).  pos_out != nullptr: idx[j] is copied to pos_out[j] as well (sets compacted in place).
 //
 // IN PLACE: outS / outL may alias the input arrays (idx, grp, gst).  A tile writes its kept
 // elements at [exclusive prefix, +kept), which never lies beyond its own input region, and it
