@@ -367,7 +367,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
         drT = arena_take<u8>(ctx, n);
         if (!nxtT[0] || !nxtT[1] || !drT) return BWTS_B200_EINTERNAL;
     }
-    u32 *whist = arena_take<u32>(ctx, 4096);  // histogram of the leading symbols of the initial keys (k_init_keys)
+    u32 *whist = arena_take<u32>(ctx, 16384);  // histogram of the leading symbols of the initial keys (k_init_keys)
     u32 *small = arena_take<u32>(ctx, 1024);  // [0] F, [1] lmax, [2] sigma, [8..15] presence, [16..] rerank counters
     u8 *code = (u8 *)arena_take<u32>(ctx, 64);
     if (!sb.k[0] || !sb.k[1] || !sb.v[0] || !sb.v[1] || !sb.hist || !sb.status || !grp || !gst || !gid || !rank || !FS ||
@@ -494,7 +494,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
     ctx->stats.initial_depth = (int)k0;
 
     // digit histograms of the initial sort from one histogram of the leading symbols (k_init_keys): possible when the
-    // widest digit spans symbols worth at most 12 bits (alphabets of 1-4, 6 and 8 bits per symbol)
+    // widest digit spans symbols worth at most 14 bits (alphabets of 1-4 and 6-8 bits per symbol; 5 bits: 15)
     u32 wsyms = 0;
     {
         const u32 k0p = k0 + (extra ? 1u : 0u), d = extra ? bits - extra : 0u;
@@ -503,11 +503,13 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             wsyms = max(wsyms, hi_bit / bits - lo_bit / bits + 1u);
         }
     }
-    const bool use_wh = !linear && g_tune_hist != 1 && wsyms * bits <= 12 && k0 >= wsyms;
+    const bool use_wh = !linear && g_tune_hist != 1 && wsyms * bits <= 14 && k0 >= wsyms;
     const u32 wbins = use_wh ? 1u << (wsyms * bits) : 0u;
     if (!linear) {
         if (use_wh) CK(cudaMemsetAsync(whist, 0, wbins * sizeof(u32), st));
-        LAUNCH_SMEM(KC_INIT_KEYS, 9.0 * n, k_init_keys, min(cdiv(n, 2048), (u32)ctx->sm_count * 6u), 256, wbins * sizeof(u32), dT, n,
+        // shared memory per CTA: 18.7 KB of staging + the histogram (4 bytes per bin, 2 above 4096 bins)
+        const size_t whb = wbins > 4096 ? wbins * 2 : wbins * sizeof(u32);
+        LAUNCH_SMEM(KC_INIT_KEYS, 9.0 * n, k_init_keys, min(cdiv(n, 2048), (u32)ctx->sm_count * (wbins > 4096 ? 4u : 6u)), 256, whb, dT, n,
                     FS, cidx, code, bits, k0, extra, sb.k[0], use_wh ? whist : (u32 *)nullptr,
                     extra + bits * (k0 - min(k0, wsyms)), wbins);
     } else {
@@ -1125,6 +1127,7 @@ extern "C" bwts_b200_ctx *bwts_b200_create(int device)
     cudaFuncSetAttribute(k_onesweep_pass<u32, 384, 12, 3, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)OsSmem<u32, 384, 12>::bytes);
     cudaFuncSetAttribute(k_onesweep_pass<u32, 384, 12, 3, 4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_init_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);  // + 18.7 KB static: above 48 KB in all
     cudaFuncSetAttribute(k_local_sort_cta_radix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LsrSmem::bytes);
     cudaFuncSetAttribute(k_local_sort_cta_radix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LsrSmem::bytes);
     cudaFuncSetAttribute(k_local_sort_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LS_CAP * sizeof(u64)));

@@ -67,7 +67,7 @@ static __device__ __forceinline__ void init_keys_flush(const u64 *s_keys, u64 *_
 // the 4 lanes per clock and SM that ATOMS sustains; copies per lane group changed nothing).  A radix digit of the
 // packed key is a bit slice of w consecutive symbols, w = 2..4 -- and the symbols t .. t+w-1 of rotation i are the
 // first w symbols of rotation i + t (cyclic inside the factor): over all i of a factor that is every rotation once.
-// So ONE histogram of the leading w symbols (`whist`, 2^(w * bits) <= 4096 bins, one shared atomic per key, taken here
+// So ONE histogram of the leading w symbols (`whist`, 2^(w * bits) <= 2^14 bins, one shared atomic per key, taken here
 // while the key is in a register) holds all eight digit histograms; k_digit_hists reads them off.
 // Grid-stride over tiles of 2048 positions: the window histogram is flushed once per CTA.
 // `extra` > 0: the bits the k0 whole symbols leave free in the 64-bit key (4 of them for 6-bit alphabets) hold the top
@@ -79,13 +79,18 @@ __global__ void __launch_bounds__(256) k_init_keys(const u8 *__restrict__ T, u32
                                                    u32 bits, u32 k0, u32 extra, u64 *__restrict__ keys,
                                                    u32 *__restrict__ whist, u32 wshift, u32 wbins)
 {
-    extern __shared__ u32 s_wh[];  // wbins words when whist != nullptr
+    // window histogram (when whist != nullptr): one word per bin up to 4096 bins; beyond (7-bit alphabets: 2^14 bins)
+    // two 16-bit counts per word, flushed every 31 tiles -- a CTA adds at most 31 * 2048 < 2^16 to a count in between
+    extern __shared__ u32 s_wh[];
     __shared__ u8 s_code[256];
     __shared__ u64 s_keys[IK_WORDS];
+    const bool wpack = wbins > 4096;
+    const u32 wwords = wpack ? wbins / 2 : wbins;
     s_code[threadIdx.x] = code[threadIdx.x];
     if (whist)
-        for (u32 b = threadIdx.x; b < wbins; b += 256) s_wh[b] = 0;
+        for (u32 b = threadIdx.x; b < wwords; b += 256) s_wh[b] = 0;
     __syncthreads();
+    u32 tiles_done = 0;
     const u32 l0 = threadIdx.x * 8;
     const u64 mask = (k0 * bits >= 64) ? ~0ull : ((1ull << (k0 * bits)) - 1);
     const u32 look = k0 + (extra ? 1u : 0u);  // symbols a key reads
@@ -108,7 +113,10 @@ __global__ void __launch_bounds__(256) k_init_keys(const u8 *__restrict__ T, u32
             u32 nextc = extra ? (u32)s_code[T[pos]] : 0u;  // symbol k0 + 1 of this rotation
             u64 full = extra ? ((key << extra) | (u64)(nextc >> pshift)) : key;
             s_keys[IK_SLOT(l0 + (i - i0))] = full;
-            if (whist) atomicAdd(&s_wh[(u32)(full >> wshift)], 1u);
+            if (whist) {
+                const u32 w = (u32)(full >> wshift);
+                if (wpack) atomicAdd(&s_wh[w >> 1], 1u << (16 * (w & 1))); else atomicAdd(&s_wh[w], 1u);
+            }
             i++;
             // slide while the window [i, i + look) stays inside the factor
             while (i < iend && i < e && (u64)i + look <= e) {
@@ -121,17 +129,38 @@ __global__ void __launch_bounds__(256) k_init_keys(const u8 *__restrict__ T, u32
                     full = key;
                 }
                 s_keys[IK_SLOT(l0 + (i - i0))] = full;
-                if (whist) atomicAdd(&s_wh[(u32)(full >> wshift)], 1u);
+                if (whist) {
+                    const u32 w = (u32)(full >> wshift);
+                    if (wpack) atomicAdd(&s_wh[w >> 1], 1u << (16 * (w & 1))); else atomicAdd(&s_wh[w], 1u);
+                }
                 i++;
             }
         }
         init_keys_flush(s_keys, keys, tile * 2048u, n);
-        __syncthreads();  // the staging rows are free again
+        __syncthreads();  // the staging rows are free again (and every count of this tile is in)
+        if (whist && wpack && ++tiles_done == 31) {
+            tiles_done = 0;
+            for (u32 b = threadIdx.x; b < wwords; b += 256) {
+                const u32 c = s_wh[b];
+                if (c) {
+                    if (c & 0xffffu) atomicAdd(whist + 2 * b, c & 0xffffu);
+                    if (c >> 16) atomicAdd(whist + 2 * b + 1, c >> 16);
+                    s_wh[b] = 0;
+                }
+            }
+            __syncthreads();
+        }
     }
     if (whist) {
-        for (u32 b = threadIdx.x; b < wbins; b += 256) {
+        for (u32 b = threadIdx.x; b < wwords; b += 256) {
             const u32 c = s_wh[b];
-            if (c) atomicAdd(whist + b, c);
+            if (!c) continue;
+            if (wpack) {
+                if (c & 0xffffu) atomicAdd(whist + 2 * b, c & 0xffffu);
+                if (c >> 16) atomicAdd(whist + 2 * b + 1, c >> 16);
+            } else {
+                atomicAdd(whist + b, c);
+            }
         }
     }
 }

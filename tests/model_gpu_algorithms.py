@@ -594,7 +594,7 @@ def initial_keys(codes, starts, bits, k0, extra=0):
 def digit_hists_from_windows(keys, bits, k0, extra=0):
     """k_init_keys' window histogram + k_digit_hists: the 256-bin histogram of every radix digit of the keys, read
     off ONE histogram of the leading `wsyms` symbols.  Returns None where the driver keeps k_radix_hist
-    (windows wider than 12 bits)."""
+    (windows wider than 14 bits)."""
     k0p, d = k0 + (1 if extra else 0), (bits - extra) if extra else 0
     P0 = -(-(k0 * bits + extra) // 8)
     span = []
@@ -602,7 +602,7 @@ def digit_hists_from_windows(keys, bits, k0, extra=0):
         lo_bit, hi_bit = 8 * p + d, min(8 * p + 7 + d, k0p * bits - 1)
         span.append(hi_bit // bits - lo_bit // bits + 1)
     wsyms = max(span)
-    if wsyms * bits > 12 or k0 < wsyms:
+    if wsyms * bits > 14 or k0 < wsyms:
         return None
     wshift = extra + bits * (k0 - wsyms)
     whist = np.bincount(np.array([k >> wshift for k in keys], dtype=np.int64), minlength=1 << (wsyms * bits))

@@ -369,6 +369,26 @@ def test_initial_sort_histograms_from_window_counts(bwts, ctx, oracle, gen):
         bwts.tune(6, 0)
 
 
+def test_window_histogram_packed_counts_do_not_overflow(bwts, ctx):
+    """7-bit alphabets count the leading symbol pairs in 16-bit halves of shared-memory words, flushed every 31
+    tiles: 48 MiB in which 99 % of the bytes are one symbol put ~62 k counts per flush on a single bin.  Checked
+    against the path without the window histogram (tune 21 = 1) and by the round trip."""
+    rng = np.random.default_rng(77)
+    n = 48 << 20
+    x = np.full(n, 120, dtype=np.uint8)
+    hits = rng.integers(0, n, size=n // 100)
+    x[hits] = rng.integers(40, 110, size=len(hits), dtype=np.uint8)   # 70 other symbols: 71 distinct bytes, 7 bits
+    x = x.tobytes()
+    got = ctx.forward_host(x)
+    assert ctx.stats()["alphabet_bits"] == 7
+    bwts.tune(21, 1)
+    try:
+        assert ctx.forward_host(x) == got
+    finally:
+        bwts.tune(21, 0)
+    assert ctx.inverse_host(got) == x
+
+
 def test_binned_rank_scatter_in_later_rounds(bwts, ctx, oracle, gen):
     """re-ranks after the first one also send their ranks through the bin pass when a third of the set's ranks moved
     in the round before (inputs of 128 Mi bytes and more; both the large-group and the small-group set); tune 7 = 4
