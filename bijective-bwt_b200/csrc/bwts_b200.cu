@@ -48,6 +48,7 @@ static long g_tune_scatterbin = 0;  // first re-rank: 0 = bin the rank scatter w
 static long g_tune_l2gran = 0;     // cudaLimitMaxL2FetchGranularity applied when a transform starts (0 = leave the device's setting)
 static long g_tune_hist = 0;       // 1 = digit histograms of the initial sort by k_radix_hist (eight shared atomics per key)
 static long g_tune_partial = 0;    // 1 = initial keys of whole symbols only (no partial symbol in the spare bits)
+static long g_tune_emitwin = 0;    // MiB of output per emit window (16..1024; 0 = 64)
 static long g_tune_ctasort = 0;    // CTA-local sort: 0 = radix in shared memory, 1 = bitonic network (round 1)
 static long g_tune_lyscan = 0;     // Lyndon chunk-minimum scan: 0 = Hillis-Steele levels under a probe budget, else CTA-wide; 1 / 2 = force either
 static long g_tune_tmode = 0;      // tuple set: 0 = one thread per member (up to 8 members), 1 = one thread per group (up to 32)
@@ -863,7 +864,7 @@ static int forward_core(bwts_b200_ctx *ctx, const u8 *dT, u32 n, u8 *d_out, i32 
             LAUNCH(KC_EMIT, 9.0 * n, k_scatter_bytes, cdiv(cdiv(n, 4), 256), 256, bin_pos, bin_val, n, d_out);
         } else {
             // rank windows of 64 Mi slots: the scatter target of one launch stays resident in the 126 MB L2
-            const u32 win = 64u << 20;
+            const u32 win = (g_tune_emitwin >= 16 && g_tune_emitwin <= 1024) ? (u32)g_tune_emitwin << 20 : 64u << 20;
             for (u64 lo = 0; lo < n; lo += win) {
                 const u32 hi = (u32)min((u64)n, lo + win);
                 LAUNCH(KC_EMIT, (lo == 0 ? 7.0 : 4.0) * n, k_emit, cdiv(cdiv(n, 4), 256), 256, dT, n, rank, flags, d_out,
@@ -1725,6 +1726,7 @@ extern "C" int bwts_b200_tune(int key, long value)
     if (key == 20) { g_tune_tmode = value; return 0; }
     if (key == 21) { g_tune_hist = value; return 0; }
     if (key == 22) { g_tune_partial = value; return 0; }
+    if (key == 23) { g_tune_emitwin = value; return 0; }
     if (key == 16) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invbudget = value; return 0; }
     if (key == 13) { if (value < 0) return BWTS_B200_EINVAL; g_tune_invq = value; return 0; }
     return BWTS_B200_EINVAL;
