@@ -160,7 +160,8 @@ const char *bwts_b200_version(void);
  * round 1 (1) instead of the radix sort in shared memory, 20 = tuple set with one thread per group and
  * groups of up to 32 (1; measured slower than one thread per member), 21 = digit histograms of the initial sort by a
  * sweep over the keys (1) instead of the window histogram taken while the keys are built, 22 = initial keys of whole
- * symbols only (1; default: spare key bits hold the top bits of the next symbol).  value 0 = default. */
+ * symbols only (1; default: spare key bits hold the top bits of the next symbol), 23 = MiB of output per emit window
+ * (16..1024; default 64: the scatter target of one sweep stays in L2).  value 0 = default. */
 int bwts_b200_tune(int key, long value);
 
 /* ---- "next" row: suffix array behind libdivsufsort's own seam ----- */
