@@ -1,6 +1,7 @@
 #!/bin/bash
 # One gpurun call's worth of measurements (scratch output under gpurun_out/); edited per call.
 # Every command runs under its own timeout: a hung kernel must not eat the box's time limit.
-out=gpurun_out/r3j; mkdir -p $out
-timeout 100 python tests/gpu_experiments.py C5 base 23:96 23:128 23:48 23:86 > $out/exp_c5.txt 2>&1
-grep "^==\|fwd emit" $out/exp_c5.txt
+out=gpurun_out/r3l; mkdir -p $out
+timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest.txt 2>&1; echo "pytest rc=$?" >> $out/pytest.txt
+python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.txt 2>&1; echo "smoke rc=$?" >> $out/smoke.txt
+tail -n 3 $out/pytest.txt; tail -n 2 $out/smoke.txt
