@@ -25,7 +25,7 @@
 #include "radix.cuh"
 #include "scan.cuh"
 
-#define BWTS_VERSION "bwts-b200 0.1 (sm_100a)"
+#define BWTS_VERSION "bwts-b200 0.2 (sm_100a)"
 
 enum KClass {
     KC_LYNDON = 0, KC_FACTORS, KC_INIT_KEYS, KC_RADIX_HIST, KC_ONESWEEP, KC_BUILD_KEYS, KC_RERANK, KC_EMIT,
