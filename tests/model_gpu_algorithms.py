@@ -556,6 +556,25 @@ def binned_scatter(pos, val, n, kb):
     return out
 
 
+def binned_scatter_counted(pos, val, rank, kb):
+    """later re-ranks: only the live positions are written, the bin starts come from a count of the positions per
+    region (k_bin_count + scan) instead of the closed form; untouched entries of rank keep their value"""
+    shift = kb - 8
+    counts = np.bincount(pos >> shift, minlength=256)
+    base = np.concatenate(([0], np.cumsum(counts)[:-1]))
+    bin_pos = np.empty_like(pos)
+    bin_val = np.empty_like(val)
+    fill = base.copy()
+    for p, v in zip(pos, val):          # the onesweep pass: stable inside a bin
+        b = p >> shift
+        bin_pos[fill[b]] = p
+        bin_val[fill[b]] = v
+        fill[b] += 1
+    out = rank.copy()
+    out[bin_pos] = bin_val              # k_scatter_pairs, region by region
+    return out
+
+
 def onesweep_tile_permutation(digits):
     """k_onesweep_pass: sorted slot -> raw position of one tile (stable by digit), built the way the
     kernel does: per-warp ranks in slot order, exclusive warp offsets per digit, digit starts"""

@@ -126,6 +126,18 @@ def test_binned_scatter_equals_direct_scatter():
         assert np.array_equal(model.binned_scatter(pos, val, n, kb), direct)
 
 
+def test_counted_bin_scatter_of_a_sparse_set_equals_direct_scatter():
+    rng = np.random.default_rng(11)
+    for n, m in ((1000, 1), (1000, 300), (70_001, 20_000), (70_001, 70_001)):
+        kb = max(8, int(n - 1).bit_length())
+        pos = rng.permutation(n)[:m].astype(np.int64)
+        val = rng.integers(0, 1 << 30, size=m)
+        rank = rng.integers(0, 1 << 30, size=n)
+        direct = rank.copy()
+        direct[pos] = val
+        assert np.array_equal(model.binned_scatter_counted(pos, val, rank, kb), direct)
+
+
 def test_onesweep_tile_permutation_is_the_stable_partition():
     rng = np.random.default_rng(10)
     for tile in (384 * 12, 100):
